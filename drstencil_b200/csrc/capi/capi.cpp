@@ -1,0 +1,762 @@
+// libdrstencil.so -- C ABI launch layer of the B200 stencil engine (see include/drstencil.h).
+//
+// plan creation  : choose_spec -> generate_tu -> NVRTC (sm_100a cubin, cached on disk)
+// first sweep    : cubin -> cuModuleLoadData, cuTensorMapEncodeTiled per buffer
+// every sweep    : one cuLaunchKernel of dr_<name>
+// There is no CPU path: without a CUDA device every compute entry point returns DRS_E_NOGPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/drstencil.h"
+#include "../core/generate.hpp"
+#include "../core/stencil.hpp"
+#include "emit_program.hpp"
+
+extern const char* const drs_embedded_header_names[];
+extern const char* const drs_embedded_header_texts[];
+extern const int drs_embedded_header_count;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// ---------------------------------------------------------------------------------------------
+// CUDA driver entry points, fetched through the (statically linked) runtime so that the library
+// loads on machines without libcuda.so.1
+// ---------------------------------------------------------------------------------------------
+struct Driver {
+    bool ok = false;
+    std::string why;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             CUstream, void**, void**) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+};
+
+Driver& driver() {
+    static Driver d;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            d.why = std::string("no CUDA device: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return;
+        }
+        cudaFree(0);  // primary context
+        auto get = [&](const char* name, void** fp) {
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint(name, fp, cudaEnableDefault, &q) != cudaSuccess || *fp == nullptr) {
+                d.why += std::string("driver entry point missing: ") + name + "; ";
+                return false;
+            }
+            return true;
+        };
+        bool ok = true;
+        ok &= get("cuModuleLoadData", (void**)&d.ModuleLoadData);
+        ok &= get("cuModuleUnload", (void**)&d.ModuleUnload);
+        ok &= get("cuModuleGetFunction", (void**)&d.ModuleGetFunction);
+        ok &= get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute);
+        ok &= get("cuFuncGetAttribute", (void**)&d.FuncGetAttribute);
+        ok &= get("cuLaunchKernel", (void**)&d.LaunchKernel);
+        ok &= get("cuTensorMapEncodeTiled", (void**)&d.TensorMapEncodeTiled);
+        ok &= get("cuGetErrorString", (void**)&d.GetErrorString);
+        d.ok = ok;
+    });
+    return d;
+}
+
+std::string cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+// ---------------------------------------------------------------------------------------------
+// NVRTC, loaded on demand
+// ---------------------------------------------------------------------------------------------
+struct Nvrtc {
+    bool ok = false;
+    std::string why;
+    void* h = nullptr;
+    typedef struct _nvrtcProgram* Prog;
+    int (*CreateProgram)(Prog*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*CompileProgram)(Prog, int, const char* const*) = nullptr;
+    int (*GetCUBINSize)(Prog, size_t*) = nullptr;
+    int (*GetCUBIN)(Prog, char*) = nullptr;
+    int (*GetProgramLogSize)(Prog, size_t*) = nullptr;
+    int (*GetProgramLog)(Prog, char*) = nullptr;
+    int (*DestroyProgram)(Prog*) = nullptr;
+    int (*Version)(int*, int*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+Nvrtc& nvrtc() {
+    static Nvrtc n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* nm : names) {
+            n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (n.h) break;
+        }
+        if (!n.h) { n.why = "libnvrtc.so.12 not found"; return; }
+        auto get = [&](const char* name) { return dlsym(n.h, name); };
+        n.CreateProgram = (decltype(n.CreateProgram))get("nvrtcCreateProgram");
+        n.CompileProgram = (decltype(n.CompileProgram))get("nvrtcCompileProgram");
+        n.GetCUBINSize = (decltype(n.GetCUBINSize))get("nvrtcGetCUBINSize");
+        n.GetCUBIN = (decltype(n.GetCUBIN))get("nvrtcGetCUBIN");
+        n.GetProgramLogSize = (decltype(n.GetProgramLogSize))get("nvrtcGetProgramLogSize");
+        n.GetProgramLog = (decltype(n.GetProgramLog))get("nvrtcGetProgramLog");
+        n.DestroyProgram = (decltype(n.DestroyProgram))get("nvrtcDestroyProgram");
+        n.Version = (decltype(n.Version))get("nvrtcVersion");
+        n.GetErrorString = (decltype(n.GetErrorString))get("nvrtcGetErrorString");
+        n.ok = n.CreateProgram && n.CompileProgram && n.GetCUBINSize && n.GetCUBIN && n.GetProgramLogSize &&
+               n.GetProgramLog && n.DestroyProgram && n.Version;
+        if (!n.ok) n.why = "libnvrtc is missing entry points";
+    });
+    return n;
+}
+
+std::string g_cache_dir;
+std::string cache_dir() {
+    if (!g_cache_dir.empty()) return g_cache_dir;
+    if (const char* e = getenv("DRS_CACHE_DIR")) return e;
+    Dl_info info;
+    if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t s = p.rfind('/');
+        return (s == std::string::npos ? std::string(".") : p.substr(0, s)) + "/_jitcache";
+    }
+    return "/tmp/drs_jitcache";
+}
+
+const char* kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=false",
+                            "-default-device"};
+
+// source -> cubin, through the on-disk cache
+int compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& key_out) {
+    std::string all = src;
+    for (int i = 0; i < drs_embedded_header_count; ++i) all += drs_embedded_header_texts[i];
+    for (const char* o : kNvrtcOpts) all += o;
+    int maj = 0, min = 0;
+    Nvrtc& n = nvrtc();
+    if (n.ok) n.Version(&maj, &min);
+    char key[64];
+    std::snprintf(key, sizeof key, "%016llx_%d_%d", (unsigned long long)drs::fnv1a(all), maj, min);
+    key_out = key;
+    const std::string dir = cache_dir();
+    const std::string path = dir + "/" + key + ".cubin";
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (f) {
+            cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+            if (!cubin.empty()) return DRS_OK;
+        }
+    }
+    if (!n.ok) return fail(DRS_E_COMPILE, "NVRTC unavailable: " + n.why);
+    Nvrtc::Prog prog = nullptr;
+    int r = n.CreateProgram(&prog, src.c_str(), "drs_generated.cu", drs_embedded_header_count,
+                            drs_embedded_header_texts, drs_embedded_header_names);
+    if (r != 0) return fail(DRS_E_COMPILE, "nvrtcCreateProgram failed");
+    r = n.CompileProgram(prog, (int)(sizeof kNvrtcOpts / sizeof kNvrtcOpts[0]), kNvrtcOpts);
+    size_t logn = 0;
+    n.GetProgramLogSize(prog, &logn);
+    std::string log(logn, '\0');
+    if (logn > 1) n.GetProgramLog(prog, &log[0]);
+    if (r != 0) {
+        n.DestroyProgram(&prog);
+        return fail(DRS_E_COMPILE, std::string("NVRTC: ") + (n.GetErrorString ? n.GetErrorString(r) : "error") + "\n" + log);
+    }
+    size_t sz = 0;
+    n.GetCUBINSize(prog, &sz);
+    cubin.resize(sz);
+    n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    mkdir(dir.c_str(), 0755);
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        f.write(cubin.data(), (std::streamsize)cubin.size());
+    }
+    rename(tmp.c_str(), path.c_str());
+    return DRS_OK;
+}
+
+// Params as the kernels see it (drs_common.cuh: struct Params) -- keep the two in step.
+struct DevParams {
+    const void* in;
+    void* out;
+    long long L, M, N;
+    long long slow_lo, slow_hi;
+    int halo;
+    int nxs, nys, nzs;
+    int chunk;
+    int* fault;
+    void* peer_lo;
+    void* peer_hi;
+    long long push_lo0, push_lo1, peer_lo_shift;
+    long long push_hi0, push_hi1, peer_hi_shift;
+};
+
+}  // namespace
+
+struct drs_stencil {
+    drs::Stencil st;
+    std::string name = "stencil";
+};
+
+struct drs_plan {
+    drs::Stencil st;         // base stencil + sizes
+    drs_knobs knobs;
+    drs::KernelSpec spec;
+    std::string source, cache_key;
+    std::vector<char> cubin;
+    // device state (bound at first use)
+    bool loaded = false;
+    int device = -1;
+    CUmodule mod = nullptr;
+    CUfunction f_sweep = nullptr, f_gold = nullptr, f_check = nullptr;
+    int regs = 0, spill = 0;
+    int* d_fault = nullptr;
+    double* d_res = nullptr;
+    std::map<const void*, CUtensorMap> tmaps;
+    void* h_dev[2] = {nullptr, nullptr};  // buffers owned by drs_run_host
+    long long launches = 0;
+    // slab mode
+    bool slab = false;
+    long long g_slow = 0, lo = 0, hi = 0;
+    void* my_bases[2] = {nullptr, nullptr};
+    void* lower_bases[2] = {nullptr, nullptr};
+    void* upper_bases[2] = {nullptr, nullptr};
+    long long lower_lo = 0, upper_lo = 0;
+
+    long long local_slow() const { return spec.dim == 3 ? st.L : st.M; }
+};
+
+namespace {
+
+int ensure_loaded(drs_plan* p) {
+    if (p->loaded) return DRS_OK;
+    Driver& d = driver();
+    if (!d.ok) return fail(DRS_E_NOGPU, "drstencil needs a CUDA device (no CPU fallback): " + d.why);
+    cudaGetDevice(&p->device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, p->device);
+    if (prop.major != 10) {
+        return fail(DRS_E_NOGPU, std::string("kernels are built for sm_100a only; device is ") + prop.name + " (sm_" +
+                                     std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    }
+    CUresult r = d.ModuleLoadData(&p->mod, p->cubin.data());
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleLoadData: " + cu_err(r));
+    const std::string nm = p->spec.name;
+    if (p->spec.tma_ok) {
+        r = d.ModuleGetFunction(&p->f_sweep, p->mod, ("dr_" + nm).c_str());
+        if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(dr_): " + cu_err(r));
+        const int smem = p->spec.smem_bytes();
+        r = d.FuncSetAttribute(p->f_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+        if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(r));
+        d.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->f_sweep);
+        d.FuncGetAttribute(&p->spill, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, p->f_sweep);
+    }
+    r = d.ModuleGetFunction(&p->f_gold, p->mod, ("gold_" + nm).c_str());
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(gold_): " + cu_err(r));
+    r = d.ModuleGetFunction(&p->f_check, p->mod, ("check_" + nm).c_str());
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(check_): " + cu_err(r));
+    if (cudaMalloc(&p->d_fault, sizeof(int)) != cudaSuccess) return fail(DRS_E_CUDA, "cudaMalloc(fault flag)");
+    cudaMemset(p->d_fault, 0, sizeof(int));
+    if (cudaMalloc(&p->d_res, 2 * sizeof(double)) != cudaSuccess) return fail(DRS_E_CUDA, "cudaMalloc(result)");
+    p->loaded = true;
+    return DRS_OK;
+}
+
+int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
+    auto it = p->tmaps.find(base);
+    if (it != p->tmaps.end()) { *out = &it->second; return DRS_OK; }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
+    const drs::KernelSpec& s = p->spec;
+    CUtensorMap m;
+    const CUtensorMapDataType dt = s.dtype == DRS_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint64_t es = (cuuint64_t)s.esize();
+    CUresult r;
+    if (s.dim == 2) {
+        cuuint64_t dims[2] = {(cuuint64_t)p->st.N, (cuuint64_t)p->st.M};
+        cuuint64_t strides[1] = {(cuuint64_t)p->st.N * es};
+        cuuint32_t box[2] = {(cuuint32_t)s.wb(), (cuuint32_t)s.rb};
+        cuuint32_t estr[2] = {1, 1};
+        r = driver().TensorMapEncodeTiled(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[3] = {(cuuint64_t)p->st.N, (cuuint64_t)p->st.M, (cuuint64_t)p->st.L};
+        cuuint64_t strides[2] = {(cuuint64_t)p->st.N * es, (cuuint64_t)p->st.N * (cuuint64_t)p->st.M * es};
+        cuuint32_t box[3] = {(cuuint32_t)s.wb(), (cuuint32_t)(s.ry + 2 * s.rj), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        r = driver().TensorMapEncodeTiled(&m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(r));
+    if (p->tmaps.size() > 64) p->tmaps.clear();
+    auto ins = p->tmaps.emplace(base, m);
+    *out = &ins.first->second;
+    return DRS_OK;
+}
+
+void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q) {
+    const drs::KernelSpec& s = p->spec;
+    std::memset(&q, 0, sizeof q);
+    q.in = in; q.out = out;
+    q.L = p->st.L; q.M = p->st.M; q.N = p->st.N;
+    q.halo = s.halo;
+    const long long slow = p->local_slow();
+    if (!p->slab) { q.slow_lo = s.halo; q.slow_hi = slow - s.halo; }
+    else {
+        const long long ghost = s.halo, org = p->lo - ghost;  // global index of local plane 0
+        const long long glo = std::max<long long>(p->lo, s.halo), ghi = std::min<long long>(p->hi, p->g_slow - s.halo);
+        q.slow_lo = glo - org; q.slow_hi = ghi - org;
+        int b = -1;
+        if (out == p->my_bases[0]) b = 0; else if (out == p->my_bases[1]) b = 1;
+        if (b >= 0 && p->lower_bases[b] && p->lo > 0) {
+            q.peer_lo = p->lower_bases[b];
+            q.push_lo0 = p->lo - org; q.push_lo1 = p->lo + ghost - org;
+            q.peer_lo_shift = org - (p->lower_lo - ghost);
+        }
+        if (b >= 0 && p->upper_bases[b] && p->hi < p->g_slow) {
+            q.peer_hi = p->upper_bases[b];
+            q.push_hi0 = p->hi - ghost - org; q.push_hi1 = p->hi - org;
+            q.peer_hi_shift = org - (p->upper_lo - ghost);
+        }
+    }
+    if (q.slow_hi < q.slow_lo) q.slow_hi = q.slow_lo;
+    const long long a0 = (s.halo / s.vec()) * s.vec();
+    const long long xspan = std::max<long long>(0, (q.N - s.halo) - a0);
+    q.nxs = (int)((xspan + s.wu() - 1) / s.wu());
+    const long long nslow = (q.slow_hi - q.slow_lo + s.chunk - 1) / s.chunk;
+    if (s.dim == 2) { q.nys = (int)nslow; q.nzs = 1; }
+    else {
+        const long long yspan = std::max<long long>(0, q.M - 2 * s.halo);
+        q.nys = (int)((yspan + s.ry - 1) / s.ry);
+        q.nzs = (int)nslow;
+    }
+    q.chunk = s.chunk;
+    q.fault = p->d_fault;
+}
+
+int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
+    DevParams q;
+    fill_params(p, in, out, q);
+    void* args[] = {&q};
+    unsigned bx = 32, by = 8, bz = 1;
+    unsigned gx = (unsigned)((q.N + bx - 1) / bx), gy = (unsigned)((q.M + by - 1) / by), gz = (unsigned)q.L;
+    CUresult r = driver().LaunchKernel(p->f_gold, gx, gy, gz, bx, by, bz, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch gold_: " + cu_err(r));
+    p->launches++;
+    return DRS_OK;
+}
+
+int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
+    if (in == out) return fail(DRS_E_ARG, "d_in and d_out must differ");
+    if (!p->spec.tma_ok) return launch_gold(p, in, out, stream);
+    CUtensorMap* tm = nullptr;
+    int rc = tensor_map_for(p, in, &tm);
+    if (rc != DRS_OK) return rc;
+    DevParams q;
+    fill_params(p, in, out, q);
+    const long long tiles = (long long)q.nxs * q.nys * q.nzs;
+    if (tiles <= 0) return DRS_OK;
+    const long long ctas = (tiles + p->spec.nw - 1) / p->spec.nw;
+    if (ctas > 0x7fffffffLL) return fail(DRS_E_ARG, "grid too large");
+    void* args[] = {tm, &q};
+    CUresult r = driver().LaunchKernel(p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
+                                       (unsigned)p->spec.smem_bytes(), (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch dr_: " + cu_err(r));
+    p->launches++;
+    return DRS_OK;
+}
+
+int check_sizes(const drs::Stencil& st) {
+    if (st.M <= 0 || st.N <= 0 || (st.dim == 3 && st.L <= 0)) return fail(DRS_E_ARG, "grid extents must be positive");
+    if (st.M > 0x7fffff00LL || st.N > 0x7fffff00LL || st.L > 0x7fffff00LL) return fail(DRS_E_ARG, "extent too large");
+    return DRS_OK;
+}
+
+int make_plan(const drs_stencil* s, const drs_knobs* k, drs_plan** out, bool compile) {
+    if (!s || !k || !out) return fail(DRS_E_ARG, "null argument");
+    int rc = check_sizes(s->st);
+    if (rc != DRS_OK) return rc;
+    drs_plan* p = new drs_plan();
+    p->st = s->st;
+    p->knobs = *k;
+    p->spec.name = s->name;
+    std::string err = drs::choose_spec(s->st, *k, p->spec);
+    if (!err.empty()) { delete p; return fail(DRS_E_ARG, err); }
+    p->source = drs::generate_tu(p->spec);
+    if (compile) {
+        rc = compile_cubin(p->source, p->cubin, p->cache_key);
+        if (rc != DRS_OK) { delete p; return rc; }
+    }
+    *out = p;
+    return DRS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void drs_knobs_default(drs_knobs* k) {
+    std::memset(k, 0, sizeof *k);
+    k->step = 1; k->dist = 0; k->streaming = 0; k->bx = 16; k->by = 16; k->sn = 16; k->stream_unroll = 4;
+    k->block_merge_x = k->block_merge_y = k->cyclic_merge_x = k->cyclic_merge_y = 1;
+    k->prefetch = 0; k->merge_forward = 5; k->check = 0;
+    k->dtype = DRS_F64; k->fuse = DRS_FUSE_TEMPORAL; k->explicit_mask = 0;
+}
+
+int drs_stencil_from_file(const char* path, int is3d, drs_stencil** out) {
+    if (!path || !out) return fail(DRS_E_ARG, "null argument");
+    drs_stencil* s = new drs_stencil();
+    if (!s->st.read_stc(path, is3d != 0)) {
+        delete s;
+        return fail(DRS_E_IO, "Error opening stencil file.");
+    }
+    // kernel name = file name minus its last four characters, as main.cpp:243-244 (directory dropped)
+    std::string nm = path;
+    size_t sl = nm.rfind('/');
+    if (sl != std::string::npos) nm = nm.substr(sl + 1);
+    if (nm.size() > 4) nm.erase(nm.size() - 4);
+    for (char& c : nm) if (!(isalnum((unsigned char)c) || c == '_')) c = '_';
+    if (nm.empty()) nm = "stencil";
+    s->name = nm;
+    *out = s;
+    return DRS_OK;
+}
+
+int drs_stencil_from_points(int dim, const int* offsets, const double* coefs, int npoints, long long L, long long M,
+                            long long N, int iterations, drs_stencil** out) {
+    if ((dim != 2 && dim != 3) || !offsets || !coefs || npoints <= 0 || !out) return fail(DRS_E_ARG, "bad stencil description");
+    drs_stencil* s = new drs_stencil();
+    s->st.set_points(dim, offsets, coefs, npoints);
+    s->st.L = dim == 3 ? L : 1; s->st.M = M; s->st.N = N; s->st.iterations = iterations;
+    *out = s;
+    return DRS_OK;
+}
+
+void drs_stencil_destroy(drs_stencil* s) { delete s; }
+
+int drs_stencil_set_name(drs_stencil* s, const char* name) {
+    if (!s || !name || !*name) return fail(DRS_E_ARG, "bad name");
+    std::string nm = name;
+    for (char& c : nm) if (!(isalnum((unsigned char)c) || c == '_')) c = '_';
+    s->name = nm;
+    return DRS_OK;
+}
+
+int drs_stencil_set_size(drs_stencil* s, long long L, long long M, long long N, int iterations) {
+    if (!s) return fail(DRS_E_ARG, "null stencil");
+    s->st.L = s->st.dim == 3 ? L : 1; s->st.M = M; s->st.N = N; s->st.iterations = iterations;
+    return DRS_OK;
+}
+
+int drs_stencil_compose(drs_stencil* s, int step) {
+    if (!s || step < 1) return fail(DRS_E_ARG, "step must be >= 1");
+    s->st.compose(step);
+    return DRS_OK;
+}
+
+int drs_stencil_size(const drs_stencil* s, long long dims[3], int* iterations) {
+    if (!s) return fail(DRS_E_ARG, "null stencil");
+    if (dims) { dims[0] = s->st.L; dims[1] = s->st.M; dims[2] = s->st.N; }
+    if (iterations) *iterations = s->st.iterations;
+    return DRS_OK;
+}
+
+int drs_stencil_terms(const drs_stencil* s, int* offsets3, double* coefs, int capacity) {
+    if (!s) return fail(DRS_E_ARG, "null stencil");
+    std::vector<drs::Term> t = s->st.terms();
+    if (offsets3 && coefs) {
+        if (capacity < (int)t.size()) return fail(DRS_E_ARG, "buffer too small");
+        for (size_t q = 0; q < t.size(); ++q) {
+            offsets3[3 * q] = t[q].dk; offsets3[3 * q + 1] = t[q].dj; offsets3[3 * q + 2] = t[q].di;
+            coefs[q] = t[q].coef;
+        }
+    }
+    return (int)t.size();
+}
+
+int drs_stencil_term_text(const drs_stencil* s, int q, char* buf, size_t buflen) {
+    if (!s || !buf || buflen == 0) return fail(DRS_E_ARG, "null argument");
+    if (q < 0 || q >= (int)s->st.points.size()) return fail(DRS_E_ARG, "term index out of range");
+    auto it = s->st.points.begin();
+    std::advance(it, q);
+    std::snprintf(buf, buflen, "%s", drs::coef_literal_text(it->second).c_str());
+    return DRS_OK;
+}
+
+int drs_stencil_analyze(const drs_stencil* s, int dist, int merge_forward, int* halo, int* dist_out, int* range,
+                        int sizes[4]) {
+    if (!s) return fail(DRS_E_ARG, "null stencil");
+    drs::Analysis a;
+    const bool ok = s->st.analyze(dist, merge_forward, a);
+    if (halo) *halo = a.halo;
+    if (dist_out) *dist_out = a.dist;
+    if (sizes) {
+        sizes[0] = (int)a.forward_slow.size(); sizes[1] = (int)a.forward_mid.size();
+        sizes[2] = (int)a.forward_fast.size(); sizes[3] = (int)a.backward.size();
+    }
+    if (!ok) return fail(DRS_E_NOREUSE, "No data to reuse. You can try another dist.");
+    if (range) *range = a.range();
+    return DRS_OK;
+}
+
+int drs_plan_create(const drs_stencil* s, const drs_knobs* k, drs_plan** out) { return make_plan(s, k, out, true); }
+
+int drs_plan_warm_cache(const drs_stencil* s, const drs_knobs* k) {
+    drs_plan* p = nullptr;
+    int rc = make_plan(s, k, &p, true);
+    if (rc == DRS_OK) delete p;
+    return rc;
+}
+
+void drs_plan_destroy(drs_plan* p) {
+    if (!p) return;
+    if (p->loaded) {
+        cudaFree(p->d_fault);
+        cudaFree(p->d_res);
+        for (void* b : p->h_dev) if (b) cudaFree(b);
+        if (p->mod) driver().ModuleUnload(p->mod);
+    }
+    delete p;
+}
+
+int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
+    if (!p || !info) return fail(DRS_E_ARG, "null argument");
+    std::memset(info, 0, sizeof *info);
+    const drs::KernelSpec& s = p->spec;
+    info->dim = s.dim; info->dtype = s.dtype; info->step = s.step; info->fuse = s.fuse;
+    info->L = p->st.L; info->M = p->st.M; info->N = p->st.N;
+    info->halo = s.halo; info->npoints = (int)s.chain.size(); info->timesteps_per_sweep = s.step;
+    info->warps_per_cta = s.nw; info->tile_x = s.wu(); info->tile_y = s.dim == 3 ? s.ry : 1;
+    info->chunk = s.chunk; info->stages = s.st; info->rows_per_stage = s.dim == 2 ? s.rb : 1;
+    DevParams q;
+    fill_params(p, nullptr, nullptr, q);
+    const long long tiles = (long long)q.nxs * q.nys * q.nzs;
+    info->grid_x = (int)((tiles + s.nw - 1) / s.nw); info->grid_y = 1; info->grid_z = 1;
+    info->block = s.nw * 32;
+    info->smem_bytes = s.tma_ok ? s.smem_bytes() : 0;
+    info->regs_per_thread = p->regs; info->spill_bytes = p->spill;
+    // computed / useful points
+    const double useful = (double)std::max<long long>(1, q.N - 2 * s.halo) * (double)std::max<long long>(1, q.slow_hi - q.slow_lo) *
+                          (s.dim == 3 ? (double)std::max<long long>(1, q.M - 2 * s.halo) : 1.0);
+    double computed;
+    if (s.dim == 2) computed = (double)q.nxs * s.wt() * ((double)(q.slow_hi - q.slow_lo) + (double)q.nys * 2 * s.ts * s.rj);
+    else computed = (double)q.nxs * s.wt() * (double)q.nys * s.ry * (double)(q.slow_hi - q.slow_lo);
+    info->redundancy = computed / useful;
+    std::snprintf(info->kernel_name, sizeof info->kernel_name, "%s%s", s.tma_ok ? "dr_" : "gold_", s.name.c_str());
+    return DRS_OK;
+}
+
+const char* drs_plan_source(const drs_plan* p) { return p ? p->source.c_str() : ""; }
+const char* drs_plan_note(const drs_plan* p) { return p ? p->spec.note.c_str() : ""; }
+const char* drs_plan_cache_key(const drs_plan* p) { return p ? p->cache_key.c_str() : ""; }
+
+int drs_sweep(drs_plan* p, const void* d_in, void* d_out, void* stream) {
+    if (!p || !d_in || !d_out) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    return launch_sweep(p, d_in, d_out, (cudaStream_t)stream);
+}
+
+int drs_gold_sweep(drs_plan* p, const void* d_in, void* d_out, void* stream) {
+    if (!p || !d_in || !d_out) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    return launch_gold(p, d_in, d_out, (cudaStream_t)stream);
+}
+
+static int run_schedule(drs_plan* p, void* a, void* b, int iterations, void* stream, int* sweeps, bool gold) {
+    if (!p || !a || !b) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) {
+        rc = gold ? launch_gold(p, a, b, (cudaStream_t)stream) : launch_sweep(p, a, b, (cudaStream_t)stream);
+        if (rc != DRS_OK) return rc;
+        rc = gold ? launch_gold(p, b, a, (cudaStream_t)stream) : launch_sweep(p, b, a, (cudaStream_t)stream);
+        if (rc != DRS_OK) return rc;
+        n += 2;
+    }
+    if (sweeps) *sweeps = n;
+    return DRS_OK;
+}
+
+int drs_run(drs_plan* p, void* d_a, void* d_b, int iterations, void* stream, int* sweeps) {
+    return run_schedule(p, d_a, d_b, iterations, stream, sweeps, false);
+}
+int drs_gold_run(drs_plan* p, void* d_a, void* d_b, int iterations, void* stream, int* sweeps) {
+    return run_schedule(p, d_a, d_b, iterations, stream, sweeps, true);
+}
+
+int drs_plan_sync_check(drs_plan* p, void* stream) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    if (!p->loaded) return DRS_OK;
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
+    int f = 0;
+    e = cudaMemcpy(&f, p->d_fault, sizeof f, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("fault flag read: ") + cudaGetErrorString(e));
+    if (f) {
+        cudaMemset(p->d_fault, 0, sizeof(int));
+        return fail(DRS_E_KERNEL, "sweep kernel pipeline watchdog fired (a TMA stage never arrived)");
+    }
+    return DRS_OK;
+}
+
+int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* device_ms) {
+    if (!p || !h_a || !h_b) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    const size_t bytes = (size_t)p->st.L * p->st.M * p->st.N * p->spec.esize();
+    for (int i = 0; i < 2; ++i)
+        if (!p->h_dev[i] && cudaMalloc(&p->h_dev[i], bytes) != cudaSuccess)
+            return fail(DRS_E_CUDA, "cudaMalloc of the sweep buffers failed");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    cudaMemcpyAsync(p->h_dev[0], h_a, bytes, cudaMemcpyHostToDevice, 0);
+    cudaMemcpyAsync(p->h_dev[1], h_b, bytes, cudaMemcpyHostToDevice, 0);
+    rc = run_schedule(p, p->h_dev[0], p->h_dev[1], iterations, nullptr, nullptr, false);
+    cudaMemcpyAsync(h_a, p->h_dev[0], bytes, cudaMemcpyDeviceToHost, 0);
+    cudaEventRecord(e1, 0);
+    int rc2 = drs_plan_sync_check(p, nullptr);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    return rc != DRS_OK ? rc : rc2;
+}
+
+int drs_check_error(drs_plan* p, const void* d_out, const void* d_ref, double res[2]) {
+    if (!p || !d_out || !d_ref || !res) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    cudaMemset(p->d_res, 0, 2 * sizeof(double));
+    DevParams q;
+    fill_params(p, d_out, nullptr, q);
+    void* args[] = {&q, (void*)&d_ref, &p->d_res};
+    unsigned bx = 32, by = 8;
+    unsigned gx = (unsigned)((q.N + bx - 1) / bx), gy = (unsigned)((q.M + by - 1) / by), gz = (unsigned)q.L;
+    CUresult r = driver().LaunchKernel(p->f_check, gx, gy, gz, bx, by, 1, 0, nullptr, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch check_: " + cu_err(r));
+    p->launches++;
+    double h[2];
+    if (cudaMemcpy(h, p->d_res, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return fail(DRS_E_CUDA, "result read failed");
+    const double cnt = (double)std::max<long long>(1, q.N - 2 * q.halo) * (double)std::max<long long>(1, q.slow_hi - q.slow_lo) *
+                       (p->spec.dim == 3 ? (double)std::max<long long>(1, q.M - 2 * q.halo) : 1.0);
+    double mx;
+    std::memcpy(&mx, &h[0], sizeof mx);
+    res[0] = mx > 1e-13 ? mx : 1e-13;   // common.hpp:53 starts the running maximum at 1e-13
+    res[1] = std::sqrt(h[1] / cnt);
+    return DRS_OK;
+}
+
+long long drs_plan_launch_count(const drs_plan* p) { return p ? p->launches : 0; }
+
+// ---- slabs -------------------------------------------------------------------------------
+int drs_plan_set_slab(drs_plan* p, long long global_slow, long long lo, long long hi) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    const long long ghost = p->spec.halo;
+    if (lo < 0 || hi <= lo || hi > global_slow) return fail(DRS_E_ARG, "bad slab range");
+    if (hi - lo + 2 * ghost != p->local_slow())
+        return fail(DRS_E_ARG, "slab arrays must hold hi - lo + 2*Halo planes along the slow axis");
+    p->slab = true; p->g_slow = global_slow; p->lo = lo; p->hi = hi;
+    return DRS_OK;
+}
+
+int drs_plan_set_peers(drs_plan* p, void* const my_bases[2], void* const lower_bases[2], void* const upper_bases[2],
+                       long long lower_lo, long long upper_lo) {
+    if (!p || !my_bases) return fail(DRS_E_ARG, "null argument");
+    if (!p->slab) return fail(DRS_E_ARG, "call drs_plan_set_slab first");
+    if (p->spec.dim != 3 || !p->spec.tma_ok) return fail(DRS_E_ARG, "fused halo push is implemented for the 3D TMA sweep");
+    for (int b = 0; b < 2; ++b) {
+        p->my_bases[b] = my_bases[b];
+        p->lower_bases[b] = lower_bases ? lower_bases[b] : nullptr;
+        p->upper_bases[b] = upper_bases ? upper_bases[b] : nullptr;
+    }
+    p->lower_lo = lower_lo; p->upper_lo = upper_lo;
+    return DRS_OK;
+}
+
+int drs_ipc_export(void* d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, d_ptr);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    std::memcpy(handle, &h, 64);
+    return DRS_OK;
+}
+int drs_ipc_import(const unsigned char handle[64], void** d_ptr) {
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    return DRS_OK;
+}
+int drs_ipc_close(void* d_ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(d_ptr);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+    return DRS_OK;
+}
+int drs_device_malloc(size_t bytes, void** d_ptr) {
+    cudaError_t e = cudaMalloc(d_ptr, bytes);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return DRS_OK;
+}
+int drs_device_free(void* d_ptr) { cudaFree(d_ptr); return DRS_OK; }
+
+// ---- emitters ----------------------------------------------------------------------------
+int drs_emit_program(const drs_stencil* s, const drs_knobs* k, const char* kernel_name, const char* path) {
+    if (!s || !k || !path) return fail(DRS_E_ARG, "null argument");
+    drs::KernelSpec spec;
+    spec.name = kernel_name && *kernel_name ? kernel_name : s->name;
+    std::string err = drs::choose_spec(s->st, *k, spec);
+    if (!err.empty()) return fail(DRS_E_ARG, err);
+    std::ofstream f(path, std::ios::out | std::ios::trunc);
+    if (!f) return fail(DRS_E_IO, std::string("cannot write ") + path);
+    f << drs::emit_program_text(s->st, *k, spec);
+    return DRS_OK;
+}
+
+const char* drs_last_error(void) { return g_err.c_str(); }
+const char* drs_version(void) { return "drstencil-b200 0.1 (sm_100a)"; }
+int drs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void drs_set_cache_dir(const char* dir) { g_cache_dir = dir ? dir : ""; }
+
+}  // extern "C"

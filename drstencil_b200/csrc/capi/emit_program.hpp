@@ -1,0 +1,182 @@
+// `drstencil -o out.cu`: a standalone CUDA program = the specialised translation unit + a main()
+// that mirrors the reference's emitted host code (/root/reference/codegen_2d.hpp:564-664,
+// codegen.hpp:547-635): rand()/(RAND_MAX-1) input, zero output, 10 warm-up launches, the
+// `for (t = 0; t < Iterations; t += 2*step)` ping-pong loop, "GPU computation time: %f ms", and
+// with --check the gold kernel run through the same schedule plus the max/RMS error lines of
+// /root/reference/common.hpp:47-102.  Scripts that grep the reference's stdout keep working.
+// Differences: sizes are 64-bit (the reference overflows `unsigned int nbytes` above 4 GiB,
+// codegen_2d.hpp:575), the timed region is bracketed by device synchronisation, and the build
+// line needs  -I <repo>/drstencil_b200/csrc/kernels  for the kernel templates.
+#pragma once
+#include <sstream>
+#include <string>
+
+#include "../core/generate.hpp"
+
+namespace drs {
+
+inline std::string emit_program_text(const Stencil& st, const drs_knobs& k, const KernelSpec& s) {
+    std::ostringstream o;
+    const char* T = s.dtype == DRS_F64 ? "double" : "float";
+    o << "// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo --fmad=false \\\n"
+         "//        -I <repo>/drstencil_b200/csrc/kernels out.cu -o out\n";
+    o << "#include <cstdio>\n#include <cstdlib>\n#include <cstring>\n#include <cmath>\n#include <sys/time.h>\n"
+         "#include <cuda.h>\n#include <cuda_runtime.h>\n";
+    o << generate_tu(s);
+    o << "\n#define GridL " << st.L << "LL\n#define GridM " << st.M << "LL\n#define GridN " << st.N << "LL\n";
+    o << "#define Iterations " << st.iterations << "\n#define Halo " << s.halo << "\n#define Step " << s.step << "\n";
+    o << "typedef " << T << " real_t;\n";
+    o << R"(
+static void check_error(const char* message) {
+    cudaError_t error = cudaGetLastError();
+    if (error != cudaSuccess) { printf("CUDA error : %s, %s\n", message, cudaGetErrorString(error)); exit(-1); }
+}
+static double get_time() {
+    struct timeval tv; gettimeofday(&tv, 0);
+    return tv.tv_sec + (double)tv.tv_usec * 1e-6;
+}
+static real_t* random_array(size_t n) {   // common.hpp:9-32
+    real_t* a = (real_t*)malloc(n * sizeof(real_t));
+    for (size_t x = 0; x < n; ++x) a[x] = (real_t)((double)rand() / (double)(RAND_MAX - 1));
+    return a;
+}
+static double check_result(const real_t* out, const real_t* ref) {   // common.hpp:47-102
+    double error = 0.0, max_error = 1e-13; long long mk = 0, mj = 0, mi = 0;
+    const long long k0 = DRS_DIM == 3 ? Halo : 0, k1 = DRS_DIM == 3 ? GridL - Halo : 1;
+    for (long long kk = k0; kk < k1; kk++)
+        for (long long j = Halo; j < GridM - Halo; j++)
+            for (long long i = Halo; i < GridN - Halo; i++) {
+                double d = (double)out[(kk * GridM + j) * GridN + i] - (double)ref[(kk * GridM + j) * GridN + i];
+                d = d < 0.0 ? -d : d;
+                error += d * d;
+                if (d > max_error) { max_error = d; mk = kk; mj = j; mi = i; }
+            }
+    if (DRS_DIM == 3) printf("[Test] Max Error : %e @ (%lld,%lld,%lld)\n", max_error, mk, mj, mi);
+    else printf("[Test] Max Error : %e @ (,%lld,%lld)\n", max_error, mj, mi);
+    return sqrt(error / ((double)(k1 - k0) * (double)(GridM - 2 * Halo) * (double)(GridN - 2 * Halo)));
+}
+)";
+    o << "static drs::Params make_params(const real_t* in, real_t* out) {\n"
+         "    drs::Params p; memset(&p, 0, sizeof p);\n"
+         "    p.in = in; p.out = out; p.L = GridL; p.M = GridM; p.N = GridN; p.halo = Halo;\n"
+         "    p.slow_lo = Halo; p.slow_hi = (DRS_DIM == 3 ? GridL : GridM) - Halo;\n";
+    o << "    const long long a0 = (Halo / " << s.vec() << ") * " << s.vec() << ";\n";
+    o << "    p.nxs = (int)(((GridN - Halo) - a0 + " << s.wu() - 1 << ") / " << s.wu() << ");\n";
+    o << "    p.chunk = " << s.chunk << ";\n";
+    o << "    const long long nslow = (p.slow_hi - p.slow_lo + p.chunk - 1) / p.chunk;\n";
+    if (s.dim == 2) o << "    p.nys = (int)nslow; p.nzs = 1;\n";
+    else o << "    p.nys = (int)((GridM - 2 * Halo + " << s.ry - 1 << ") / " << s.ry << "); p.nzs = (int)nslow;\n";
+    o << "    return p;\n}\n";
+    o << R"(
+static int* g_fault = 0;
+static void gold_launch(const real_t* in, real_t* out) {
+    drs::Params p = make_params(in, out);
+    dim3 block(32, 8, 1), grid((unsigned)((GridN + 31) / 32), (unsigned)((GridM + 7) / 8), (unsigned)GridL);
+    DRS_GOLD_NAME<<<grid, block>>>(p);
+}
+)";
+    if (s.tma_ok) {
+        o << "static CUtensorMap make_map(const real_t* base) {\n"
+             "    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,\n"
+             "        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,\n"
+             "        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);\n"
+             "    static encode_t encode = 0;\n"
+             "    if (!encode) { cudaDriverEntryPointQueryResult q; cudaFree(0);\n"
+             "        cudaGetDriverEntryPoint(\"cuTensorMapEncodeTiled\", (void**)&encode, cudaEnableDefault, &q);\n"
+             "        if (!encode) { printf(\"CUDA error : cuTensorMapEncodeTiled unavailable\\n\"); exit(-1); } }\n"
+             "    CUtensorMap m;\n";
+        o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
+        if (s.dim == 2) {
+            o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
+            o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
+            o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+        } else {
+            o << "    cuuint64_t dims[3] = {(cuuint64_t)GridN, (cuuint64_t)GridM, (cuuint64_t)GridL};\n"
+                 "    cuuint64_t strides[2] = {(cuuint64_t)GridN * sizeof(real_t), (cuuint64_t)GridN * GridM * sizeof(real_t)};\n";
+            o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.ry + 2 * s.rj << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
+            o << "    CUresult r = encode(&m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+        }
+        o << "        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
+             "    if (r != CUDA_SUCCESS) { printf(\"CUDA error : cuTensorMapEncodeTiled failed (%d)\\n\", (int)r); exit(-1); }\n"
+             "    return m;\n}\n";
+        o << "static void dr_launch(const real_t* in, real_t* out) {\n"
+             "    static CUtensorMap maps[2]; static const real_t* bases[2] = {0, 0};\n"
+             "    int b = (bases[0] == in) ? 0 : (bases[1] == in) ? 1 : (bases[0] == 0 ? 0 : 1);\n"
+             "    if (bases[b] != in) { maps[b] = make_map(in); bases[b] = in; }\n"
+             "    drs::Params p = make_params(in, out); p.fault = g_fault;\n"
+             "    const long long tiles = (long long)p.nxs * p.nys * p.nzs;\n";
+        o << "    const unsigned ctas = (unsigned)((tiles + " << s.nw - 1 << ") / " << s.nw << ");\n";
+        o << "    drs::TensorMap tm; memcpy(&tm, &maps[b], sizeof tm);\n";
+        o << "    DRS_NAME<<<ctas, " << s.nw * 32 << ", " << s.smem_bytes() << ">>>(tm, p);\n}\n";
+    } else {
+        o << "static void dr_launch(const real_t* in, real_t* out) { gold_launch(in, out); }\n";
+    }
+    o << R"(
+int main(int argc, char** argv)
+{
+    puts("Initiating ...");
+    const size_t count = (size_t)GridL * GridM * GridN, nbytes = count * sizeof(real_t);
+    real_t* h_in = random_array(count);
+    real_t* h_out = (real_t*)calloc(count, sizeof(real_t));
+    real_t *in, *out;
+    cudaMalloc(&in, nbytes);
+    check_error("Failed to allocate device memory for in.\n");
+    cudaMemcpy(in, h_in, nbytes, cudaMemcpyHostToDevice);
+    cudaMalloc(&out, nbytes);
+    check_error("Failed to allocate device memory for out.\n");
+    cudaMemcpy(out, h_out, nbytes, cudaMemcpyHostToDevice);
+    cudaMalloc(&g_fault, sizeof(int)); cudaMemset(g_fault, 0, sizeof(int));
+)";
+    if (s.tma_ok)
+        o << "    cudaFuncSetAttribute(DRS_NAME, cudaFuncAttributeMaxDynamicSharedMemorySize, " << s.smem_bytes() << ");\n";
+    o << R"(
+    puts("GPU computing ...");
+    for (int i = 0; i < 10; i++) dr_launch(in, out);   // warm up
+    cudaDeviceSynchronize();
+    double startTime = get_time();
+    for (int t = 0; t < Iterations; t += 2 * Step) {
+        dr_launch(in, out);
+        dr_launch(out, in);
+    }
+    cudaDeviceSynchronize();
+    double endTime = get_time();
+    check_error("Kernel error");
+    puts("GPU finished computing.");
+    printf("GPU computation time: %f ms\n", 1000 * (endTime - startTime));
+)";
+    if (k.check) {
+        o << R"(
+    puts("Checking error ...");
+    real_t *g_in, *g_out;
+    cudaMalloc(&g_in, nbytes);
+    check_error("Failed to allocate device memory for g_in.\n");
+    cudaMemcpy(g_in, h_in, nbytes, cudaMemcpyHostToDevice);
+    cudaMalloc(&g_out, nbytes);
+    check_error("Failed to allocate device memory for g_out.\n");
+    cudaMemcpy(g_out, h_out, nbytes, cudaMemcpyHostToDevice);
+    for (int t = 0; t < Iterations; t += 2 * Step) {
+        gold_launch(g_in, g_out);
+        gold_launch(g_out, g_in);
+    }
+    cudaDeviceSynchronize();
+    check_error("Kernel(gold) error");
+    cudaMemcpy(h_out, in, nbytes, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_in, g_in, nbytes, cudaMemcpyDeviceToHost);
+    double error = check_result(h_out, h_in);
+    printf("[Test] RMS Error: %e\n", error);
+    cudaFree(g_in);
+    cudaFree(g_out);
+)";
+    }
+    o << R"(
+    free(h_in);
+    free(h_out);
+    cudaFree(in);
+    cudaFree(out);
+    return 0;
+}
+)";
+    return o.str();
+}
+
+}  // namespace drs

@@ -1,0 +1,197 @@
+// Kernel specialisation: (stencil, knobs) -> launch geometry + the CUDA C++ translation unit
+// that instantiates the hand-written sm_100a templates in ../kernels/ for exactly this stencil.
+//
+// This is the engine's replacement for the reference's emitters
+//   /root/reference/codegen_2d.hpp  (codeGen_2d::header_gen / gpu_code_gen* / gold_gpu_code_gen)
+//   /root/reference/codegen.hpp     (codeGen::...)
+// The reference prints a whole kernel per configuration; here the kernel bodies are fixed
+// templates and the generator only prints the stencil-specific part: the ordered mul/fma chain
+// with literal coefficients, the operator extents and the tile/pipeline constants.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/drstencil.h"
+#include "stencil.hpp"
+
+namespace drs {
+
+struct KernelSpec {
+    // problem
+    int dim = 2, dtype = DRS_F64, step = 1, fuse = DRS_FUSE_TEMPORAL;
+    int ts = 1;                 // sub-steps evaluated per sweep inside the kernel
+    int halo = 0;               // frozen ring (reference macro Halo) = step * order(base)
+    int rk = 0, rj = 0, e = 0;  // extents of the operator one sub-step evaluates
+    std::vector<Term> chain;    // that operator, gold (std::map) order
+    std::vector<Term> gold;     // the composed operator, gold order
+    // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
+    int nw = 2, st = 4, rb = 4, ry = 8, minb = 1, chunk = 128;
+    bool tma_ok = true;         // false -> rows not 16-byte multiples: naive kernel does the sweep
+    std::string name = "stencil";
+    std::string note;           // why a requested mode was changed, for logs
+
+    int vec() const { return dtype == DRS_F64 ? 2 : 4; }
+    int esize() const { return dtype == DRS_F64 ? 8 : 4; }
+    int e0() const { return (e + vec() - 1) / vec() * vec(); }
+    int hw() const { return ((ts - 1) * e + vec() - 1) / vec() * vec(); }
+    int wt() const { return 32 * vec(); }
+    int wu() const { return dim == 2 ? wt() - 2 * hw() : wt(); }
+    int wb() const { return wt() + 2 * e0(); }
+    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * (ry + 2 * rj) * esize(); }
+    int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
+    int smem_bytes() const { return nw * st * stage_stride() + nw * st * 8; }
+};
+
+inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+inline int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+inline bool knob_given(const drs_knobs& k, int bit) { return (k.explicit_mask >> bit) & 1; }
+enum KnobBit { KB_STEP = 0, KB_DIST, KB_STREAMING, KB_BX, KB_BY, KB_SN, KB_UNROLL, KB_BMX, KB_BMY, KB_CMX, KB_CMY,
+               KB_PREFETCH, KB_MERGE_FWD, KB_CHECK, KB_DTYPE, KB_FUSE };
+
+// Chooses the specialisation.  Returns "" or an error text (-> DRS_E_ARG).
+//
+// How the reference's knobs (main.cpp:12-56) map onto this engine when given explicitly:
+//   --step n          temporal depth (sub-steps per sweep), or composed operator with --fuse algebraic
+//   --sn n            slow-axis outputs per warp tile (rows in 2D, planes in 3D)
+//   --bx x --by y     CTA size: x*y/32 warps (2D --streaming: x/32, as the reference ignores by there)
+//   --stream-unroll u rows per TMA stage in 2D (rounded down to a power of two)
+//   --prefetch        ring depth: 8 stages instead of 4 (the TMA ring *is* the prefetch)
+//   --block-merge-y / --cyclic-merge-y m   3D: rows per thread = 4*m
+//   --streaming, --dist, --merge-forward, merge-x: accepted; the first is always on, the
+//                     others only matter to the reference's forward/backward partition
+// Knobs not given explicitly fall back to B200 heuristics, not to the reference's defaults
+// (bx = by = sn = 16 describe an sm_80 thread block, not a warp pipeline).
+inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, KernelSpec& s) {
+    if (k.step < 1) return "step must be >= 1";
+    if (base_in.step != 1) return "plan needs the un-composed stencil (step is a plan knob)";
+    Stencil st = base_in;
+    s.dim = st.dim;
+    s.dtype = k.dtype;
+    s.step = k.step;
+    s.fuse = k.fuse;
+    const int order = st.order_of(st.base);
+    const int radius = Stencil::radius_of(st.base);
+    if (st.base.empty()) return "stencil has no points";
+    if (radius > order)
+        return "an offset exceeds Halo (the largest positive slow-axis offset): the reference would read across "
+               "rows there (drstencil_2d.hpp:82-92); unsupported";
+    s.halo = order * k.step;
+    Stencil comp = st;
+    comp.compose(k.step);
+    s.gold = comp.terms();
+    const int vec = s.vec();
+    bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
+    if (temporal && s.dim == 3) { temporal = false; s.note = "3D temporal blocking not available: composed operator used"; }
+    if (temporal) {
+        int emax = 0;
+        for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
+        if (emax > vec) { temporal = false; s.note = "x extent exceeds one vector: composed operator used"; }
+        else if (32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) < vec) {
+            temporal = false; s.note = "depth leaves no useful columns per warp: composed operator used";
+        }
+    }
+    if (temporal) { s.ts = k.step; s.chain = st.base_terms(); }
+    else { s.ts = 1; s.chain = s.gold; s.fuse = k.step > 1 ? DRS_FUSE_ALGEBRAIC : k.fuse; }
+    s.rk = s.rj = s.e = 0;
+    for (const Term& t : s.chain) {
+        s.rk = std::max(s.rk, std::abs(t.dk));
+        s.rj = std::max(s.rj, std::abs(t.dj));
+        s.e = std::max(s.e, std::abs(t.di));
+    }
+    // --- geometry ---
+    const long long slow = s.dim == 3 ? st.L : st.M;
+    const long long slow_out = std::max<long long>(1, slow - 2 * s.halo);
+    if (s.dim == 2) {
+        s.nw = 2; s.st = 4; s.rb = 4;
+        s.chunk = 128;
+        const int win_regs = s.ts * (2 * s.rj + 1) * (vec + 2 * s.e) * (s.esize() / 4);
+        const int est = win_regs + 48;
+        s.minb = std::max(1, std::min(16, 65536 / (std::min(est, 255) * s.nw * 32)));
+    } else {
+        s.nw = 2; s.ry = 8; s.chunk = 64;
+        s.st = pow2_ceil(2 * s.rk + 2);
+        if (s.st < 4) s.st = 4;
+        const int q_regs = (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4);
+        const int est = q_regs + 64;
+        s.minb = std::max(1, std::min(16, 65536 / (std::min(est, 255) * s.nw * 32)));
+    }
+    if (knob_given(k, KB_SN) && k.sn > 0) s.chunk = k.sn;
+    if (knob_given(k, KB_BX) || knob_given(k, KB_BY)) {
+        int threads = (s.dim == 2 && k.streaming) ? k.bx : k.bx * k.by;
+        s.nw = std::max(1, std::min(16, threads / 32));
+    }
+    if (s.dim == 2 && knob_given(k, KB_UNROLL) && k.stream_unroll > 0) s.rb = std::min(64, pow2_floor(k.stream_unroll));
+    if (knob_given(k, KB_PREFETCH) && k.prefetch) s.st = std::max(s.st, 8);
+    if (s.dim == 3) {
+        const int my = std::max(k.block_merge_y, k.cyclic_merge_y);
+        if ((knob_given(k, KB_BMY) || knob_given(k, KB_CMY)) && my >= 1) s.ry = std::min(32, 4 * my);
+    }
+    // reserved[] carries engine-only tuning overrides (the tuner's extra axes); 0 = keep
+    if (k.reserved[0] > 0) s.st = pow2_ceil(k.reserved[0]);
+    if (k.reserved[1] > 0) s.minb = k.reserved[1];
+    if (k.reserved[2] > 0) s.nw = k.reserved[2];
+    if (k.reserved[3] > 0 && s.dim == 3) s.ry = k.reserved[3];
+    if (k.reserved[4] > 0 && s.dim == 2) s.rb = pow2_floor(k.reserved[4]);
+    if (s.dim == 3 && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);
+    if (s.chunk > slow_out) s.chunk = (int)slow_out;
+    if (s.chunk < 1) s.chunk = 1;
+    while (s.smem_bytes() > 227 * 1024 && s.nw > 1) s.nw /= 2;
+    while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
+    if (s.smem_bytes() > 227 * 1024) return "tile does not fit in shared memory";
+    // TMA needs 16-byte row pitch
+    s.tma_ok = (st.N % vec) == 0;
+    return "";
+}
+
+inline void emit_chain(std::ostringstream& o, const char* macro, const std::vector<Term>& terms) {
+    // nvcc contracts t1 + t2 + ... + tP (gold order) into mul(t2), fma(t1), fma(t3) ... fma(tP);
+    // the chain is emitted in that order so that results match the reference's gold kernel bit
+    // for bit.  P == 1 is a single product.
+    o << "#define " << macro << "(MUL, FMA)";
+    std::vector<int> order;
+    if (terms.size() == 1) order = {0};
+    else { order = {1, 0}; for (int q = 2; q < (int)terms.size(); ++q) order.push_back(q); }
+    bool first = true;
+    for (int q : order) {
+        const Term& t = terms[q];
+        o << " \\\n    " << (first ? "MUL" : "FMA") << "(" << t.dk << ", " << t.dj << ", " << t.di << ", "
+          << coef_literal_text(t.coef) << ")";
+        first = false;
+    }
+    o << "\n";
+}
+
+// The specialised translation unit (kernel templates are #included by name and resolved from
+// the headers embedded in libdrstencil.so, or from -I .../csrc/kernels for emitted programs).
+inline std::string generate_tu(const KernelSpec& s) {
+    std::ostringstream o;
+    o << "// generated by drstencil-b200 for sm_100a -- stencil '" << s.name << "', " << (s.dim == 3 ? "3D" : "2D")
+      << ", " << (s.dtype == DRS_F64 ? "fp64" : "fp32") << ", step " << s.step << " ("
+      << (s.ts > 1 ? "temporal" : (s.step > 1 ? "algebraic" : "single")) << ")\n";
+    o << "#define DRS_DIM " << s.dim << "\n";
+    o << "#define DRS_T " << (s.dtype == DRS_F64 ? "double" : "float") << "\n";
+    o << "#define DRS_NAME dr_" << s.name << "\n";
+    o << "#define DRS_GOLD_NAME gold_" << s.name << "\n";
+    o << "#define DRS_CHECK_NAME check_" << s.name << "\n";
+    o << "#define DRS_HALO " << s.halo << "\n";
+    o << "#define DRS_TS " << s.ts << "\n";
+    o << "#define DRS_RK " << s.rk << "\n#define DRS_RJ " << s.rj << "\n#define DRS_E " << s.e << "\n";
+    o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
+    o << "#define DRS_RY " << s.ry << "\n#define DRS_MINB " << s.minb << "\n";
+    emit_chain(o, "DRS_CHAIN", s.chain);
+    emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
+    if (s.tma_ok) o << "#include \"" << (s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
+    o << "#include \"drs_gold.cuh\"\n";
+    return o.str();
+}
+
+inline uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+
+}  // namespace drs

@@ -1,0 +1,141 @@
+// drs_common.cuh -- device-side building blocks shared by the sm_100a sweep kernels.
+// Compiles under NVRTC (no host headers) and under nvcc (emitted standalone programs).
+//
+// The sweep kernels replace the reference's emitted dr_<name> kernels
+// (/root/reference/codegen_2d.hpp:149-561, codegen.hpp:143-544).  Where the reference stages
+// rows/planes with LDG -> STS -> __syncthreads -> LDS and writes every output twice
+// (STG + atomicAdd), these kernels let the TMA unit fill a per-warp ring of shared-memory
+// stages (mbarrier-tracked, no block-wide barrier anywhere), keep the slow-axis window in
+// registers, exchange fast-axis neighbours of intermediate time levels with warp shuffles, and
+// store each output exactly once with 128-bit stores.
+#pragma once
+
+#ifndef DRS_T
+#error "DRS_T (element type) must be defined by the generated translation unit"
+#endif
+
+typedef unsigned int drs_u32;
+typedef unsigned long long drs_u64;
+typedef long long drs_i64;
+
+namespace drs {
+
+typedef DRS_T real;
+constexpr int kVec = 16 / (int)sizeof(real);  // elements per 128-bit access: 2 (f64) or 4 (f32)
+
+struct __align__(64) TensorMap { drs_u64 opaque[16]; };  // CUtensorMap, encoded on the host
+
+// Kernel parameters common to the 2D and 3D sweeps (sizes are runtime values: unlike the
+// reference, which bakes L/M/N in as macros, one compiled plan serves any grid size).
+struct Params {
+    const real* in;
+    real* out;
+    drs_i64 L, M, N;        // local array extents (3D: L planes of M rows of N), N contiguous
+    drs_i64 slow_lo, slow_hi;  // output range along the slow axis (rows in 2D, planes in 3D)
+    int halo;                  // frozen ring width in the other axes (reference macro Halo)
+    int nxs, nys, nzs;         // tiles per axis (x strips, y tiles / row chunks, plane chunks)
+    int chunk;                 // slow-axis outputs per tile (the reference's Sn)
+    int* fault;                // device flag set when a pipeline wait times out
+    // slab mode (multi-GPU, slow-axis decomposition): output planes z in [push_lo0, push_lo1) are
+    // also stored into the lower neighbour's ghost planes, at plane z + peer_lo_shift of its
+    // array (peer_lo = that array's base, mapped over NVLink); likewise push_hi* / peer_hi.
+    real* peer_lo;
+    real* peer_hi;
+    drs_i64 push_lo0, push_lo1, peer_lo_shift;
+    drs_i64 push_hi0, push_hi1, peer_hi_shift;
+};
+
+__device__ __forceinline__ drs_u32 smem_u32(const void* p) {
+    return (drs_u32)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(drs_u64* bar, drs_u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy
+// (TMA) accesses to the same locations
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(drs_u64* bar, drs_u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(drs_u64* bar, drs_u32 parity) {
+    drs_u32 ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ drs_u64 global_ns() {
+    drs_u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a TMA that never lands (bad descriptor, driver fault) raises the fault flag after
+// ~1 s and lets the kernel run to completion instead of hanging the GPU.  Callers return at once
+// when this yields false.
+__device__ __forceinline__ bool mbar_wait(drs_u64* bar, drs_u32 parity, int* fault) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const drs_u64 t0 = global_ns();
+    for (;;) {
+        #pragma unroll 1
+        for (int spin = 0; spin < 64; ++spin)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (global_ns() - t0 > 1000000000ull || (fault && *(volatile int*)fault)) break;
+    }
+    if (fault) atomicExch(fault, 1);
+    return false;
+}
+
+// TMA tile loads: global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map, int x, int y, drs_u64* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int x, int y, int z, drs_u64* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// Explicitly rounded arithmetic: the evaluation order of a stencil expression is part of the
+// result, so nothing is left to the compiler's contraction rules.
+__device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double rfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// 128-bit shared loads / global stores of kVec elements
+__device__ __forceinline__ void lds_vec(real (&v)[kVec], const real* p) {
+    if constexpr (sizeof(real) == 8) {
+        double2 t = *reinterpret_cast<const double2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+}
+__device__ __forceinline__ void stg_vec(real* p, const real (&v)[kVec]) {
+    if constexpr (sizeof(real) == 8) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+}  // namespace drs

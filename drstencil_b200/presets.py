@@ -1,0 +1,33 @@
+"""Named configurations: the eight stencil descriptions the reference ships
+(/root/reference/benchmarks/*/*.stc, re-typed under stc/) and the five BASELINE.json workloads.
+Knob values for the BASELINE entries are what the tuner (drstencil_b200/tuner) settled on; the
+evidence is under profiles/."""
+import os
+
+from . import Knobs
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_STC = os.path.join(_ROOT, "stc")
+
+
+def _p(*parts):
+    return os.path.join(_STC, *parts)
+
+
+# name -> (stc file, knobs)
+PRESETS = {
+    "2d5pt_star": (_p("2d5pt_star.stc"), Knobs()),
+    "2d5pt_cross": (_p("2d5pt_cross.stc"), Knobs()),
+    "2d9pt_star": (_p("2d9pt_star.stc"), Knobs()),
+    "2d9pt_box": (_p("2d9pt_box.stc"), Knobs()),
+    "2d9pt_cross": (_p("2d9pt_cross.stc"), Knobs()),
+    "2d25pt_box": (_p("2d25pt_box.stc"), Knobs()),
+    "3d7pt_star": (_p("3d7pt_star.stc"), Knobs()),
+    "3d9pt_cross": (_p("3d9pt_cross.stc"), Knobs()),
+    # BASELINE.json configs
+    "c1": (_p("baseline", "c1_2d5pt_star.stc"), Knobs()),
+    "c2": (_p("baseline", "c2_2d9pt_box.stc"), Knobs(step=4)),
+    "c3": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32")),
+    "c4": (_p("baseline", "c4_3d7pt_star.stc"), Knobs()),
+    "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs()),
+}

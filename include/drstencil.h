@@ -1,0 +1,187 @@
+/*
+ * drstencil.h -- C ABI of the B200-native stencil engine (libdrstencil.so).
+ *
+ * The reference (simple86/DRStencil) has no library boundary: its "API" is the generator CLI
+ * (/root/reference/main.cpp:10-280), the text of the emitted .cu (codegen_2d.hpp:49-75,
+ * codegen.hpp:47-71) with the kernel `__global__ void dr_<name>(double*, double*)`
+ * (codegen_2d.hpp:154,461; codegen.hpp:148) and the host loop the emitted main() runs around it
+ * (codegen_2d.hpp:564-664; codegen.hpp:547-635).  Each entry point below names the piece of
+ * that flow it stands in for.  Plain pointers and sizes only; every function returns 0 on
+ * success or a negative DRS_E_* code and never calls exit(); drs_last_error() gives the text.
+ *
+ * Threading: a drs_stencil / drs_plan may be used by one host thread at a time; different
+ * objects are independent.  Device buffers are caller-owned (any allocator: cudaMalloc, torch).
+ */
+#ifndef DRSTENCIL_H_
+#define DRSTENCIL_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRS_OK 0
+#define DRS_E_ARG (-1)        /* bad argument / unsupported description                        */
+#define DRS_E_IO (-2)         /* .stc unreadable (reference: "Error opening stencil file.", rc 255) */
+#define DRS_E_NOREUSE (-3)    /* reference: "No data to reuse. You can try another dist.", rc 1    */
+#define DRS_E_CONFIG (-4)     /* reference: "Invalid configuration!", rc 255                     */
+#define DRS_E_COMPILE (-5)    /* kernel specialisation failed (NVRTC log in drs_last_error)      */
+#define DRS_E_CUDA (-6)       /* CUDA driver/runtime error                                      */
+#define DRS_E_NOGPU (-7)      /* no usable CUDA device: the engine has NO CPU fallback          */
+#define DRS_E_KERNEL (-8)     /* kernel reported an internal fault (pipeline watchdog)          */
+
+#define DRS_F64 0
+#define DRS_F32 1             /* extension: the reference is fp64 only                          */
+
+#define DRS_FUSE_TEMPORAL 0   /* --step n = n in-kernel sub-steps of the base operator          */
+#define DRS_FUSE_ALGEBRAIC 1  /* --step n = the composed (fused) operator evaluated literally,   */
+                              /*            exactly what the reference emits                    */
+
+typedef struct drs_stencil drs_stencil; /* DRStencil_2d / DRStencil (drstencil_2d.hpp:14-45, drstencil.hpp:14-49) */
+typedef struct drs_plan drs_plan;       /* one specialised, compiled sweep == one emitted dr_<name> + its launch shape */
+
+/* The generator's command-line knobs, same names and defaults as main.cpp:12-56.
+ * drs_knobs_default() fills the reference defaults; fields after `check` are extensions. */
+typedef struct drs_knobs {
+    int step;          /* --step            1  */
+    int dist;          /* --dist            0 = derive */
+    int streaming;     /* --streaming       0  */
+    int bx, by;        /* --bx --by         16 16 */
+    int sn;            /* --sn              16 */
+    int stream_unroll; /* --stream-unroll   4  */
+    int block_merge_x, block_merge_y;   /* 1 1 */
+    int cyclic_merge_x, cyclic_merge_y; /* 1 1 */
+    int prefetch;      /* --prefetch        0  */
+    int merge_forward; /* --merge-forward   5  */
+    int check;         /* --check           0  */
+    /* extensions */
+    int dtype;         /* --dtype f64|f32   DRS_F64 */
+    int fuse;          /* --fuse temporal|algebraic   DRS_FUSE_TEMPORAL */
+    int explicit_mask; /* bit i set: knob i (in the order above, step = bit 0) was given explicitly;
+                          knobs not given explicitly are chosen by the engine's B200 heuristics */
+    int reserved[7];
+} drs_knobs;
+
+/* Geometry the engine chose for a plan (for logs, the tuner and bench.py). */
+typedef struct drs_plan_info {
+    int dim, dtype, step, fuse;
+    long long L, M, N;
+    int halo;              /* Halo macro: ring left untouched per sweep                       */
+    int npoints;           /* points of the operator one sub-step evaluates                   */
+    int timesteps_per_sweep;
+    int warps_per_cta, tile_x, tile_y, chunk, stages, rows_per_stage;
+    int grid_x, grid_y, grid_z, block;
+    int smem_bytes, regs_per_thread, spill_bytes;
+    double redundancy;     /* computed points / useful points                                 */
+    char kernel_name[96];
+} drs_plan_info;
+
+void drs_knobs_default(drs_knobs *k);
+
+/* ---- stencil description: replaces get_stencil / fusing / dataReuse -------------------- */
+
+/* drstencil_2d.hpp:48-73, drstencil.hpp:52-78 */
+int drs_stencil_from_file(const char *stc_path, int is3d, drs_stencil **out);
+/* same object from memory: offsets = npoints x dim ints, slowest axis first ((j,i) or (k,j,i)) */
+int drs_stencil_from_points(int dim, const int *offsets, const double *coefs, int npoints,
+                            long long L, long long M, long long N, int iterations, drs_stencil **out);
+void drs_stencil_destroy(drs_stencil *s);
+/* kernel identifier suffix: dr_<name>, gold_<name>.  From a file it is the file name minus its last
+ * four characters (main.cpp:243-244,264-265); from points it defaults to "stencil". */
+int drs_stencil_set_name(drs_stencil *s, const char *name);
+int drs_stencil_set_size(drs_stencil *s, long long L, long long M, long long N, int iterations);
+/* drstencil_2d.hpp:231-251 (fusing) -- composes the base operator `step` times (step >= 1) */
+int drs_stencil_compose(drs_stencil *s, int step);
+/* sizes: dims[0..2] = L, M, N ; returns iterations through *iterations */
+int drs_stencil_size(const drs_stencil *s, long long dims[3], int *iterations);
+/* current (composed) operator in evaluation order; offsets written as npoints x 3 (k, j, i);
+ * coefs are the doubles denoted by the 6-significant-digit literals the reference would print
+ * (drstencil_2d.hpp:174).  Pass NULL buffers to query the count.  Returns npoints or < 0. */
+int drs_stencil_terms(const drs_stencil *s, int *offsets3, double *coefs, int capacity);
+/* coefficient literal text of term q ("%g"), for emitters and tests */
+int drs_stencil_term_text(const drs_stencil *s, int q, char *buf, size_t buflen);
+/* drstencil_2d.hpp:82-97,180-228,254-269: Halo, Dist, Range and partition sizes.
+ * sizes[0..3] = |forward_slow|, |forward_mid| (3D forward_j), |forward_fast| (forward_i), |backward|.
+ * Returns DRS_E_NOREUSE when the reference would stop with "No data to reuse". */
+int drs_stencil_analyze(const drs_stencil *s, int dist, int merge_forward, int *halo, int *dist_out,
+                        int *range, int sizes[4]);
+
+/* ---- plan: replaces codeGen_2d::output / codeGen::output + nvcc ------------------------- */
+
+/* Specialises and compiles the sm_100a sweep kernel for (stencil, knobs).  The stencil must be
+ * un-composed; knobs->step selects the depth.  Needs no GPU until the first sweep. */
+int drs_plan_create(const drs_stencil *s, const drs_knobs *k, drs_plan **out);
+void drs_plan_destroy(drs_plan *p);
+int drs_plan_get_info(const drs_plan *p, drs_plan_info *info);
+/* the CUDA C++ translation unit that was specialised (what `drstencil -o` writes, minus main()) */
+const char *drs_plan_source(const drs_plan *p);
+/* why a requested mode was changed (e.g. temporal -> composed operator), "" if it was not */
+const char *drs_plan_note(const drs_plan *p);
+/* key of the compiled cubin in the on-disk cache (<cache dir>/<key>.cubin) */
+const char *drs_plan_cache_key(const drs_plan *p);
+
+/* one `dr_<name><<<grid, block>>>(d_in, d_out)` (codegen_2d.hpp:606): advances the interior
+ * [Halo, dim-Halo) by `step` timesteps; the Halo ring of d_out is not written.  d_in != d_out.
+ * `stream` is a cudaStream_t (NULL = default stream). */
+int drs_sweep(drs_plan *p, const void *d_in, void *d_out, void *stream);
+/* one `gold_<name><<<...>>>` (codegen_2d.hpp:666-688, codegen.hpp:637-660): the naive
+ * one-thread-per-point evaluation of the composed operator, for on-device self-checks */
+int drs_gold_sweep(drs_plan *p, const void *d_in, void *d_out, void *stream);
+/* the emitted host loop (codegen_2d.hpp:610-613): for (t = 0; t < iterations; t += 2*step)
+ * { sweep(A,B); sweep(B,A); } -- result is in A.  Writes the number of sweeps to *sweeps. */
+int drs_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int *sweeps);
+/* same schedule with the gold kernel (codegen_2d.hpp:638-642) */
+int drs_gold_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int *sweeps);
+/* the whole emitted main() data path on HOST buffers (codegen_2d.hpp:572-583,604-619,647):
+ * H2D of a and b, the schedule, D2H of a.  h_a/h_b hold L*M*N elements of the plan's dtype. */
+int drs_run_host(drs_plan *p, void *h_a, void *h_b, int iterations, float *device_ms);
+/* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
+ * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
+int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);
+/* waits for `stream` and reports DRS_E_KERNEL if a sweep's pipeline watchdog fired (the sweep
+ * entry points themselves never synchronise) */
+int drs_plan_sync_check(drs_plan *p, void *stream);
+/* number of kernels this plan has launched since creation (bench.py's gpu_launches) */
+long long drs_plan_launch_count(const drs_plan *p);
+
+/* ---- slab decomposition along the slowest axis (extension; the reference is single-GPU) -- */
+
+/* Declares that this plan's arrays are a slab: planes (3D) / rows (2D) [lo, hi) of a global grid
+ * with `global_slow` planes, stored with `ghost` = step*radius extra planes on each side, i.e.
+ * the local array holds (hi - lo + 2*ghost) planes.  The global frozen ring applies only at the
+ * global faces.  Must be called before the first sweep. */
+int drs_plan_set_slab(drs_plan *p, long long global_slow, long long lo, long long hi);
+/* Fused halo push (3D): while sweeping into my_bases[b], the kernel stores its boundary planes a
+ * second time, straight into the neighbours' ghost planes over NVLink.  lower_bases / upper_bases
+ * are the *neighbours' array bases* (same ping-pong order, mapped into this process with
+ * drs_ipc_import), NULL where there is no neighbour; lower_lo / upper_lo are the neighbours' first
+ * owned global planes (their `lo`). */
+int drs_plan_set_peers(drs_plan *p, void *const my_bases[2], void *const lower_bases[2],
+                       void *const upper_bases[2], long long lower_lo, long long upper_lo);
+/* CUDA IPC plumbing so that one process per GPU can map a neighbour's buffer.  Buffers to be
+ * exported must come from drs_device_malloc (a whole cudaMalloc allocation). */
+int drs_device_malloc(size_t bytes, void **d_ptr);
+int drs_device_free(void *d_ptr);
+int drs_ipc_export(void *d_ptr, unsigned char handle[64]);
+int drs_ipc_import(const unsigned char handle[64], void **d_ptr);
+int drs_ipc_close(void *d_ptr);
+
+/* ---- emitters: replaces `drstencil -o out.cu` ------------------------------------------- */
+
+/* Writes a standalone CUDA program (kernel specialisation + main() with the reference's stdout
+ * lines, codegen_2d.hpp:571,602,617-618,624,650) to `path`. */
+int drs_emit_program(const drs_stencil *s, const drs_knobs *k, const char *kernel_name, const char *path);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char *drs_last_error(void);
+const char *drs_version(void);
+int drs_device_count(void);
+/* pre-compiles without a GPU and stores the cubin in the on-disk cache (build step) */
+int drs_plan_warm_cache(const drs_stencil *s, const drs_knobs *k);
+void drs_set_cache_dir(const char *dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRSTENCIL_H_ */
