@@ -572,7 +572,7 @@ int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
     const double useful = (double)std::max<long long>(1, q.N - 2 * s.halo) * (double)std::max<long long>(1, q.slow_hi - q.slow_lo) *
                           (s.dim == 3 ? (double)std::max<long long>(1, q.M - 2 * s.halo) : 1.0);
     double computed;
-    if (s.dim == 2) computed = (double)q.nxs * s.wt() * ((double)(q.slow_hi - q.slow_lo) + (double)q.nys * 2 * s.ts * s.rj);
+    if (s.dim == 2) computed = (double)q.nxs * s.wt() * ((double)(q.slow_hi - q.slow_lo) + (double)q.nys * s.ts * (2 * s.rj + 1));
     else computed = (double)q.nxs * s.wt() * (double)q.nys * s.ry * (double)(q.slow_hi - q.slow_lo);
     info->redundancy = computed / useful;
     std::snprintf(info->kernel_name, sizeof info->kernel_name, "%s%s", s.tma_ok ? "dr_" : "gold_", s.name.c_str());

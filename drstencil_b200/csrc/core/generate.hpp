@@ -108,16 +108,10 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     if (s.dim == 2) {
         s.nw = 2; s.st = 4; s.rb = 4;
         s.chunk = 128;
-        const int win_regs = s.ts * (2 * s.rj + 1) * (vec + 2 * s.e) * (s.esize() / 4);
-        const int est = win_regs + 48;
-        s.minb = std::max(1, std::min(16, 65536 / (std::min(est, 255) * s.nw * 32)));
     } else {
         s.nw = 2; s.ry = 8; s.chunk = 64;
         s.st = pow2_ceil(2 * s.rk + 2);
         if (s.st < 4) s.st = 4;
-        const int q_regs = (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4);
-        const int est = q_regs + 64;
-        s.minb = std::max(1, std::min(16, 65536 / (std::min(est, 255) * s.nw * 32)));
     }
     if (knob_given(k, KB_SN) && k.sn > 0) s.chunk = k.sn;
     if (knob_given(k, KB_BX) || knob_given(k, KB_BY)) {
@@ -132,10 +126,18 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     // reserved[] carries engine-only tuning overrides (the tuner's extra axes); 0 = keep
     if (k.reserved[0] > 0) s.st = pow2_ceil(k.reserved[0]);
-    if (k.reserved[1] > 0) s.minb = k.reserved[1];
     if (k.reserved[2] > 0) s.nw = k.reserved[2];
     if (k.reserved[3] > 0 && s.dim == 3) s.ry = k.reserved[3];
     if (k.reserved[4] > 0 && s.dim == 2) s.rb = pow2_floor(k.reserved[4]);
+    {
+        // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
+        // per SM is the most that budget allows (never forces spills)
+        const int live = s.dim == 2 ? s.ts * (2 * s.rj + 1) * (vec + 2 * s.e) * (s.esize() / 4)
+                                    : (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4);
+        const int est = std::min(255, live + (s.dim == 2 ? 56 : 72));
+        s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
+    }
+    if (k.reserved[1] > 0) s.minb = k.reserved[1];
     if (s.dim == 3 && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);
     if (s.chunk > slow_out) s.chunk = (int)slow_out;
     if (s.chunk < 1) s.chunk = 1;

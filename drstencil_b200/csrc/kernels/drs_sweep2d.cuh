@@ -14,7 +14,8 @@
 //   * `--step n` in temporal mode runs n sub-steps per sweep: level s of the register
 //     window holds rows of time level s; x neighbours of levels >= 1 come from the adjacent
 //     lanes by warp shuffle, so a warp loses E columns per level at each edge and strips
-//     overlap by 2*HW columns;
+//     overlap by 2*HW columns; the levels of one iteration are evaluated top-down so that
+//     their chains are independent of each other;
 //   * every output is produced by one explicitly ordered mul/fma chain (DRS_CHAIN, gold
 //     order: drstencil_2d.hpp:164-178) and stored once (no STG + atomicAdd double touch,
 //     codegen_2d.hpp:345-366), with a 128-bit store where the vector is fully interior.
@@ -59,37 +60,30 @@ struct Tile {
     real* out;
 };
 
+// One iteration of the row pipeline.  Levels are evaluated TOP-DOWN: level s reads the window of
+// level s-1 as the previous iteration left it, so the TS chains of one iteration are mutually
+// independent (instruction-level parallelism across time levels) and the shared-memory loads of
+// the new input row are off the critical path.  The price is one iteration of delay per level:
+// the row produced for level s at iteration n is  yrow0 + n - s*(RJ + 1).
 template <int PH>
 __device__ __forceinline__ void row_step(real (&w)[TS][R2][VW], const real* __restrict__ srow, const Tile& t,
                                          int n) {
-    // ---- level 0: this thread's vector plus E halo columns each side, from the staged row ----
-    {
-        const real* own = srow + E0 + t.lane * kVec;
-        real tmp[kVec];
-        lds_vec(tmp, own);
+    constexpr int PP = (PH + R2 - 1) % R2;   // phase the windows were left in by the previous iteration
 #pragma unroll
-        for (int v = 0; v < kVec; ++v) w[0][PH][E + v] = tmp[v];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            w[0][PH][e] = own[e - E];
-            w[0][PH][E + kVec + e] = own[kVec + e];
-        }
-    }
-    // ---- levels 1..TS: each consumes the window of the level below ----
-#pragma unroll
-    for (int s = 1; s <= TS; ++s) {
+    for (int s = TS; s >= 1; --s) {
         real o[kVec];
 #pragma unroll
         for (int v = 0; v < kVec; ++v) {
             real acc;
-#define DRS_MUL_(dk, dj, di, c) acc = rmul(w[s - 1][slot<PH>(dj)][E + v + (di)], (real)(c));
-#define DRS_FMA_(dk, dj, di, c) acc = rfma(w[s - 1][slot<PH>(dj)][E + v + (di)], (real)(c), acc);
+#define DRS_MUL_(dk, dj, di, c) acc = rmul(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c));
+#define DRS_FMA_(dk, dj, di, c) acc = rfma(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c), acc);
             DRS_CHAIN(DRS_MUL_, DRS_FMA_)
 #undef DRS_MUL_
 #undef DRS_FMA_
             o[v] = acc;
         }
         if (s < TS) {
+            // becomes the newest row of level s; x neighbours from the adjacent lanes
 #pragma unroll
             for (int v = 0; v < kVec; ++v) w[s < TS ? s : 0][PH][E + v] = o[v];
 #pragma unroll
@@ -106,6 +100,19 @@ __device__ __forceinline__ void row_step(real (&w)[TS][R2][VW], const real* __re
                 for (int v = 0; v < kVec; ++v)
                     if (v >= t.v_lo && v < t.v_hi) dst[v] = o[v];
             }
+        }
+    }
+    // ---- level 0: this thread's vector plus E halo columns each side, from the staged row ----
+    {
+        const real* own = srow + E0 + t.lane * kVec;
+        real tmp[kVec];
+        lds_vec(tmp, own);
+#pragma unroll
+        for (int v = 0; v < kVec; ++v) w[0][PH][E + v] = tmp[v];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            w[0][PH][e] = own[e - E];
+            w[0][PH][E + kVec + e] = own[kVec + e];
         }
     }
 }
@@ -186,7 +193,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const int X0 = (H / kVec) * kVec + xs * WU - HW;   // column of lane 0, element 0
     const drs_i64 ya = p.slow_lo + (drs_i64)yc * p.chunk;
     const drs_i64 yb = (ya + p.chunk < p.slow_hi) ? ya + p.chunk : p.slow_hi;
-    st.NIT = (int)(yb - ya) + 2 * TS * RJ;
+    st.NIT = (int)(yb - ya) + TS * R2;   // + pipeline depth: one window height per level
     st.NCH = (st.NIT + RB - 1) / RB;
     st.yrow0 = (int)(ya - TS * RJ);
     st.x_box = X0 - E0;
@@ -200,8 +207,8 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         t.v_lo = (int)(lo - t.x_first);
         t.v_hi = (int)(hi - t.x_first);
     }
-    t.n_first = 2 * TS * RJ;
-    t.y_out0 = ya - 2 * TS * RJ;
+    t.n_first = TS * R2;
+    t.y_out0 = ya - TS * R2;
     t.N = p.N;
     t.out = p.out;
 

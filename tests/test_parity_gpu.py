@@ -1,0 +1,221 @@
+"""Parity of the CUDA sweep (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): fp64 with the FMA order matched -> bit-exact; temporal depth > 1
+-> max relative error <= 1e-12 (fp64) / <= 1e-5 (fp32) after the whole schedule."""
+import numpy as np
+import pytest
+
+from helpers import SHIPPED, max_rel, oracle_run, oracle_terms, stc_path
+
+pytestmark = pytest.mark.gpu
+
+SHAPES_2D = [(200, 264), (130, 150), (67, 64), (33, 1000), (1030, 36)]
+SHAPES_3D = [(40, 48, 72), (19, 21, 66), (70, 9, 130)]
+
+
+def _dev(a):
+    import torch
+    return torch.from_numpy(a).cuda()
+
+
+def _plan(name, shape, **kn):
+    import drstencil_b200 as drs
+    st = drs.Stencil.from_file(stc_path(name)).set_size(shape)
+    return drs.Plan(st, drs.Knobs(**kn))
+
+
+def _sweeps(plan, A, B, n):
+    bufs = [A, B]
+    for s in range(n):
+        plan.sweep(bufs[s & 1], bufs[(s & 1) ^ 1])
+    plan.sync_check()
+
+
+@pytest.mark.parametrize("name", SHIPPED)
+def test_single_step_fp64_bit_exact(built, name):
+    from oracle import oracle
+    shapes = SHAPES_3D if name.startswith("3d") else SHAPES_2D
+    for shape in shapes:
+        plan = _plan(name, shape)
+        assert plan.info.kernel_name.startswith("dr_")
+        a0 = oracle.rand_array(shape)
+        A, B = _dev(a0), _dev(np.full(shape, -3.0))
+        _sweeps(plan, A, B, 2)
+        refA, refB = a0.copy(), np.full(shape, -3.0)
+        offs, coefs, halo = oracle_terms(name, 1)
+        oracle.sweep(refA, refB, offs, coefs, halo)
+        oracle.sweep(refB, refA, offs, coefs, halo)
+        assert np.array_equal(B.cpu().numpy(), refB), (name, shape, "sweep 1")
+        assert np.array_equal(A.cpu().numpy(), refA), (name, shape, "sweep 2")
+
+
+@pytest.mark.parametrize("name,step", [("2d5pt_star", 2), ("2d9pt_box", 2), ("2d9pt_box", 4), ("2d5pt_cross", 2),
+                                       ("2d25pt_box", 2), ("3d7pt_star", 2), ("3d9pt_cross", 2)])
+def test_algebraic_fusion_fp64_bit_exact(built, name, step):
+    """--fuse algebraic evaluates the composed operator literally: same chain as the reference's
+    emitted gold kernel, hence bit-exact."""
+    shape = (40, 48, 72) if name.startswith("3d") else (200, 264)
+    plan = _plan(name, shape, step=step, fuse="algebraic")
+    from oracle import oracle
+    a0 = oracle.rand_array(shape)
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    _sweeps(plan, A, B, 2)
+    refA, refB = oracle_run(name, step, shape, 2)
+    assert np.array_equal(B.cpu().numpy(), refB)
+    assert np.array_equal(A.cpu().numpy(), refA)
+
+
+@pytest.mark.parametrize("name,step", [("2d5pt_star", 2), ("2d5pt_star", 3), ("2d9pt_box", 2), ("2d9pt_box", 4),
+                                       ("2d9pt_star", 2), ("2d25pt_box", 2), ("2d5pt_cross", 2), ("2d9pt_cross", 2)])
+def test_temporal_blocking_fp64_within_1e12(built, name, step):
+    for shape in [(200, 264), (131, 70), (64, 600)]:
+        plan = _plan(name, shape, step=step)
+        assert plan.note == ""
+        assert "#define DRS_TS %d" % step in plan.source
+        from oracle import oracle
+        a0 = oracle.rand_array(shape)
+        A, B = _dev(a0), _dev(np.zeros(shape))
+        n = plan.run(A, B, iterations=4 * step)
+        plan.sync_check()
+        assert n == 4
+        refA, refB = oracle_run(name, step, shape, 4)
+        H = plan.halo
+        inner = (slice(H, -H), slice(H, -H))
+        assert max_rel(A.cpu().numpy()[inner], refA[inner]) <= 1e-12, (name, step, shape)
+        # the frozen ring keeps the reference's alternating contents
+        got = A.cpu().numpy()
+        ring = np.ones(shape, bool)
+        ring[inner] = False
+        assert np.array_equal(got[ring], refA[ring])
+
+
+@pytest.mark.parametrize("name", ["2d5pt_star", "2d9pt_box", "2d25pt_box", "2d9pt_star", "3d7pt_star"])
+def test_fp32_bit_exact_and_within_1e5_of_fp64(built, name):
+    from oracle import oracle
+    shape = (40, 48, 72) if name.startswith("3d") else (200, 264)
+    plan = _plan(name, shape, dtype="f32")
+    a64 = oracle.rand_array(shape)
+    a0 = a64.astype(np.float32)
+    A, B = _dev(a0), _dev(np.zeros(shape, np.float32))
+    _sweeps(plan, A, B, 4)
+    ref32, _ = oracle_run(name, 1, shape, 4, np.float32, a0=a0)
+    assert np.array_equal(A.cpu().numpy(), ref32)
+    ref64, _ = oracle_run(name, 1, shape, 4, np.float64, a0=a64)
+    H = plan.halo
+    inner = tuple(slice(H, -H) for _ in shape)
+    assert max_rel(A.cpu().numpy()[inner], ref64[inner]) <= 1e-5
+
+
+def test_fp32_temporal_within_1e5(built):
+    from oracle import oracle
+    shape = (300, 520)
+    plan = _plan("2d25pt_box", shape, dtype="f32", step=2)
+    a64 = oracle.rand_array(shape)
+    A, B = _dev(a64.astype(np.float32)), _dev(np.zeros(shape, np.float32))
+    plan.run(A, B, iterations=4)
+    plan.sync_check()
+    ref64, _ = oracle_run("2d25pt_box", 2, shape, 2, np.float64, a0=a64)
+    H = plan.halo
+    inner = (slice(H, -H), slice(H, -H))
+    assert max_rel(A.cpu().numpy()[inner], ref64[inner]) <= 1e-5
+
+
+@pytest.mark.parametrize("name,kn", [
+    ("2d5pt_star", dict(sn=7)), ("2d5pt_star", dict(sn=1000, stages=2, rows_per_stage=1)),
+    ("2d9pt_box", dict(step=3, sn=16, warps=4, stages=8, rows_per_stage=8)),
+    ("2d25pt_box", dict(streaming=1, bx=128, sn=33, prefetch=1)),
+    ("3d7pt_star", dict(sn=5, rows_3d=4)), ("3d7pt_star", dict(sn=64, rows_3d=16, warps=1, stages=8)),
+    ("3d9pt_cross", dict(bx=32, by=4, sn=9)),
+])
+def test_knob_variants_keep_parity(built, name, kn):
+    from oracle import oracle
+    shape = (40, 48, 72) if name.startswith("3d") else (150, 200)
+    plan = _plan(name, shape, **kn)
+    step = kn.get("step", 1)
+    a0 = oracle.rand_array(shape)
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    _sweeps(plan, A, B, 2)
+    refA, refB = oracle_run(name, step, shape, 2)
+    if step == 1:
+        assert np.array_equal(A.cpu().numpy(), refA)
+    else:
+        assert max_rel(A.cpu().numpy(), refA) <= 1e-12
+
+
+def test_odd_row_pitch_takes_the_naive_kernel(built):
+    """Rows that are not a multiple of 16 bytes cannot be described to TMA: the plan falls back
+    to the naive GPU kernel (still the CUDA path, still bit-exact)."""
+    from oracle import oracle
+    shape = (50, 63)
+    plan = _plan("2d9pt_box", shape)
+    assert plan.info.kernel_name.startswith("gold_")
+    a0 = oracle.rand_array(shape)
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    _sweeps(plan, A, B, 2)
+    refA, _ = oracle_run("2d9pt_box", 1, shape, 2)
+    assert np.array_equal(A.cpu().numpy(), refA)
+
+
+@pytest.mark.parametrize("name,step", [("2d9pt_box", 4), ("3d7pt_star", 2), ("2d25pt_box", 1)])
+def test_gold_kernel_is_the_oracle_chain(built, name, step):
+    """drs_gold_sweep (K4/K5 stand-in) == oracle, bit for bit, for the composed operator."""
+    from oracle import oracle
+    shape = (40, 48, 72) if name.startswith("3d") else (120, 136)
+    plan = _plan(name, shape, step=step)
+    a0 = oracle.rand_array(shape)
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    n = plan.gold_run(A, B, iterations=2 * step)
+    assert n == 2
+    refA, _ = oracle_run(name, step, shape, 2)
+    assert np.array_equal(A.cpu().numpy(), refA)
+
+
+def test_check_error_matches_common_hpp(built):
+    from oracle import oracle
+    shape = (90, 100)
+    plan = _plan("2d5pt_star", shape)
+    rng = np.random.default_rng(5)
+    x = rng.random(shape)
+    y = x + rng.normal(0, 1e-9, shape)
+    mx, rms = plan.check_error(_dev(x), _dev(y))
+    emx, erms, _ = oracle.check_error(x, y, 1)
+    assert abs(mx - emx) <= 1e-18 and abs(rms - erms) <= 1e-6 * erms
+    mx, rms = plan.check_error(_dev(x), _dev(x))
+    assert mx == 1e-13 and rms == 0.0
+
+
+def test_run_host_round_trip(built):
+    """The emitted main()'s data path on host buffers == oracle schedule."""
+    import torch
+    from oracle import oracle
+    shape = (256, 320)
+    plan = _plan("2d5pt_star", shape)
+    a = torch.from_numpy(oracle.rand_array(shape)).pin_memory()
+    b = torch.zeros(shape, dtype=torch.float64).pin_memory()
+    ms = plan.run_host(a, b, iterations=10)
+    assert ms > 0
+    refA, _ = oracle_run("2d5pt_star", 1, shape, 10)
+    assert np.array_equal(a.numpy(), refA)
+
+
+def test_linearity_and_idempotence_at_scale(built):
+    """Size-independent properties at a BASELINE size (4096^2): sweep(a*x + y) == a*sweep(x) + sweep(y)
+    up to rounding, and a sweep is idempotent on its destination."""
+    import torch
+    shape = (4096, 4096)
+    plan = _plan("2d5pt_star", shape)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(shape, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.rand(shape, dtype=torch.float64, device="cuda", generator=g)
+    ox, oy, oz = (torch.zeros_like(x) for _ in range(3))
+    plan.sweep(x, ox); plan.sweep(y, oy); plan.sweep(2.0 * x + y, oz)
+    plan.sync_check()
+    assert torch.max(torch.abs(oz - (2.0 * ox + oy))).item() < 1e-14 * 4
+    o2 = ox.clone()
+    plan.sweep(x, o2)
+    plan.sync_check()
+    assert torch.equal(o2, ox)
+    # checksum against the gold kernel on the same input
+    og = torch.zeros_like(x)
+    plan.gold_sweep(x, og)
+    assert torch.equal(og, ox)
