@@ -159,12 +159,12 @@ _KNOB_DEFAULTS = dict(step=1, dist=0, streaming=0, bx=16, by=16, sn=16, stream_u
 class Knobs:
     """The generator's options (main.cpp:12-56), same names, same defaults.  Only options passed
     explicitly constrain the engine; the rest are chosen for B200.  Engine-only tuning overrides:
-    stages, min_blocks, warps, rows_3d (RY), rows_per_stage."""
+    stages, min_blocks, warps, rows_3d (RY), rows_per_stage, vectors (128-bit vectors per thread, 2D)."""
 
     def __init__(self, **kw):
         self.values = dict(_KNOB_DEFAULTS)
         self.explicit = set()
-        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0)
+        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0, vectors=0)
         for k, v in kw.items():
             self.set(k, v)
 
@@ -203,6 +203,7 @@ class Knobs:
         k.reserved[2] = self.extra["warps"]
         k.reserved[3] = self.extra["rows_3d"]
         k.reserved[4] = self.extra["rows_per_stage"]
+        k.reserved[5] = self.extra["vectors"]
         return k
 
     def __repr__(self):

@@ -156,7 +156,7 @@ std::string cache_dir() {
 }
 
 const char* kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=false",
-                            "-default-device"};
+                            "-default-device", "--ptxas-options=-v"};
 
 // source -> cubin, through the on-disk cache
 int compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& key_out) {
@@ -198,6 +198,10 @@ int compile_cubin(const std::string& src, std::vector<char>& cubin, std::string&
     n.GetCUBIN(prog, cubin.data());
     n.DestroyProgram(&prog);
     mkdir(dir.c_str(), 0755);
+    {
+        std::ofstream lf(dir + "/" + key + ".log");
+        lf << log.c_str();
+    }
     const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
     {
         std::ofstream f(tmp, std::ios::binary);

@@ -28,7 +28,7 @@ struct KernelSpec {
     std::vector<Term> chain;    // that operator, gold (std::map) order
     std::vector<Term> gold;     // the composed operator, gold order
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
-    int nw = 2, st = 4, rb = 4, ry = 8, minb = 1, chunk = 128;
+    int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
     bool tma_ok = true;         // false -> rows not 16-byte multiples: naive kernel does the sweep
     std::string name = "stencil";
     std::string note;           // why a requested mode was changed, for logs
@@ -37,7 +37,8 @@ struct KernelSpec {
     int esize() const { return dtype == DRS_F64 ? 8 : 4; }
     int e0() const { return (e + vec() - 1) / vec() * vec(); }
     int hw() const { return ((ts - 1) * e + vec() - 1) / vec() * vec(); }
-    int wt() const { return 32 * vec(); }
+    int cols() const { return (dim == 2 ? vt : 1) * vec(); }   // consecutive columns per thread
+    int wt() const { return 32 * cols(); }
     int wu() const { return dim == 2 ? wt() - 2 * hw() : wt(); }
     int wb() const { return wt() + 2 * e0(); }
     int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * (ry + 2 * rj) * esize(); }
@@ -60,6 +61,7 @@ enum KnobBit { KB_STEP = 0, KB_DIST, KB_STREAMING, KB_BX, KB_BY, KB_SN, KB_UNROL
 //   --bx x --by y     CTA size: x*y/32 warps (2D --streaming: x/32, as the reference ignores by there)
 //   --stream-unroll u rows per TMA stage in 2D (rounded down to a power of two)
 //   --prefetch        ring depth: 8 stages instead of 4 (the TMA ring *is* the prefetch)
+//   --block-merge-x m  2D: 128-bit vectors of adjacent columns per thread (1 or 2)
 //   --block-merge-y / --cyclic-merge-y m   3D: rows per thread = 4*m
 //   --streaming, --dist, --merge-forward, merge-x: accepted; the first is always on, the
 //                     others only matter to the reference's forward/backward partition
@@ -90,7 +92,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         int emax = 0;
         for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
         if (emax > vec) { temporal = false; s.note = "x extent exceeds one vector: composed operator used"; }
-        else if (32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) < vec) {
+        else if (32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) < vec) {   // (vt = 1 worst case)
             temporal = false; s.note = "depth leaves no useful columns per warp: composed operator used";
         }
     }
@@ -108,6 +110,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     if (s.dim == 2) {
         s.nw = 2; s.st = 4; s.rb = 4;
         s.chunk = 128;
+        s.vt = 1;
     } else {
         s.nw = 2; s.ry = 8; s.chunk = 64;
         s.st = pow2_ceil(2 * s.rk + 2);
@@ -120,6 +123,9 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     if (s.dim == 2 && knob_given(k, KB_UNROLL) && k.stream_unroll > 0) s.rb = std::min(64, pow2_floor(k.stream_unroll));
     if (knob_given(k, KB_PREFETCH) && k.prefetch) s.st = std::max(s.st, 8);
+    if (s.dim == 2 && knob_given(k, KB_BMX) && k.block_merge_x >= 1) s.vt = std::min(2, k.block_merge_x);
+    if (k.reserved[5] > 0 && s.dim == 2) s.vt = std::min(2, k.reserved[5]);
+    if (s.dim == 2 && s.wb() > 256) s.vt = 1;   // a TMA box is at most 256 elements wide
     if (s.dim == 3) {
         const int my = std::max(k.block_merge_y, k.cyclic_merge_y);
         if ((knob_given(k, KB_BMY) || knob_given(k, KB_CMY)) && my >= 1) s.ry = std::min(32, 4 * my);
@@ -132,7 +138,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     {
         // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
         // per SM is the most that budget allows (never forces spills)
-        const int live = s.dim == 2 ? s.ts * (2 * s.rj + 1) * (vec + 2 * s.e) * (s.esize() / 4)
+        const int live = s.dim == 2 ? s.ts * (2 * s.rj + 1) * (s.cols() + 2 * s.e) * (s.esize() / 4)
                                     : (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4);
         const int est = std::min(255, live + (s.dim == 2 ? 56 : 72));
         s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
@@ -183,7 +189,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_TS " << s.ts << "\n";
     o << "#define DRS_RK " << s.rk << "\n#define DRS_RJ " << s.rj << "\n#define DRS_E " << s.e << "\n";
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
-    o << "#define DRS_RY " << s.ry << "\n#define DRS_MINB " << s.minb << "\n";
+    o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
     emit_chain(o, "DRS_CHAIN", s.chain);
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
     if (s.tma_ok) o << "#include \"" << (s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";

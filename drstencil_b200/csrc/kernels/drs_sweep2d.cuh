@@ -10,7 +10,8 @@
 //     no bounds logic on the load side;
 //   * the row window the reference keeps in shared memory (`in_shm[Range][...]`,
 //     codegen_2d.hpp:166-172) lives in registers, rotated statically (the row loop is
-//     unrolled by the window height), each thread owning one 128-bit vector of columns;
+//     unrolled by the window height), each thread owning DRS_VT 128-bit vectors of adjacent
+//     columns (the reference's --block-merge-x);
 //   * `--step n` in temporal mode runs n sub-steps per sweep: level s of the register
 //     window holds rows of time level s; x neighbours of levels >= 1 come from the adjacent
 //     lanes by warp shuffle, so a warp loses E columns per level at each edge and strips
@@ -21,7 +22,7 @@
 //     codegen_2d.hpp:345-366), with a 128-bit store where the vector is fully interior.
 //
 // Generated translation unit must define: DRS_T DRS_NAME DRS_RJ DRS_E DRS_TS
-// DRS_CHAIN(MUL,FMA) DRS_NW DRS_ST DRS_RB DRS_MINB.
+// DRS_CHAIN(MUL,FMA) DRS_NW DRS_ST DRS_RB DRS_VT DRS_MINB.
 #pragma once
 #include "drs_common.cuh"
 
@@ -32,10 +33,12 @@ constexpr int RJ = DRS_RJ;          // max |dj| of the sub-step operator
 constexpr int E = DRS_E;            // max |di|
 constexpr int TS = DRS_TS;          // sub-steps (time levels) per sweep
 constexpr int R2 = 2 * RJ + 1;      // register window height
-constexpr int VW = kVec + 2 * E;    // register window width per thread
+constexpr int VT = DRS_VT;          // 128-bit vectors per thread (the reference's --block-merge-x)
+constexpr int C = VT * kVec;        // consecutive columns a thread owns
+constexpr int VW = C + 2 * E;       // register window width per thread
 constexpr int E0 = ((E + kVec - 1) / kVec) * kVec;               // smem halo columns per side
 constexpr int HW = (((TS - 1) * E + kVec - 1) / kVec) * kVec;    // strip overlap per side
-constexpr int WT = 32 * kVec;       // columns a warp computes per row
+constexpr int WT = 32 * C;          // columns a warp computes per row
 constexpr int WU = WT - 2 * HW;     // columns it stores
 constexpr int WB = WT + 2 * E0;     // TMA box width
 constexpr int ST = DRS_ST, RB = DRS_RB, NW = DRS_NW;
@@ -43,7 +46,8 @@ constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);
 constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
 static_assert((ST & (ST - 1)) == 0 && (RB & (RB - 1)) == 0, "stages and rows/stage are powers of two");
-static_assert(TS == 1 || E <= kVec, "shuffle exchange reaches one lane");
+static_assert(TS == 1 || E <= C, "shuffle exchange reaches one lane");
+static_assert(WB <= 256, "TMA box is at most 256 elements wide");
 static_assert(WU > 0, "strip overlap leaves no useful columns");
 
 // physical slot of the window row at offset dj when the newest row sits in slot PH
@@ -56,6 +60,7 @@ struct Tile {
     int v_lo, v_hi;    // storable elements of the vector: v_lo <= v < v_hi
     drs_i64 y_out0;    // output row produced at iteration 0 (may lie before the chunk)
     int n_first;       // first iteration whose output row is inside the chunk
+    int n_end;         // one past the last such iteration
     drs_i64 N;
     real* out;
 };
@@ -71,9 +76,9 @@ __device__ __forceinline__ void row_step(real (&w)[TS][R2][VW], const real* __re
     constexpr int PP = (PH + R2 - 1) % R2;   // phase the windows were left in by the previous iteration
 #pragma unroll
     for (int s = TS; s >= 1; --s) {
-        real o[kVec];
+        real o[C];
 #pragma unroll
-        for (int v = 0; v < kVec; ++v) {
+        for (int v = 0; v < C; ++v) {
             real acc;
 #define DRS_MUL_(dk, dj, di, c) acc = rmul(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c));
 #define DRS_FMA_(dk, dj, di, c) acc = rfma(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c), acc);
@@ -85,34 +90,43 @@ __device__ __forceinline__ void row_step(real (&w)[TS][R2][VW], const real* __re
         if (s < TS) {
             // becomes the newest row of level s; x neighbours from the adjacent lanes
 #pragma unroll
-            for (int v = 0; v < kVec; ++v) w[s < TS ? s : 0][PH][E + v] = o[v];
+            for (int v = 0; v < C; ++v) w[s < TS ? s : 0][PH][E + v] = o[v];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                w[s < TS ? s : 0][PH][e] = __shfl_up_sync(0xffffffffu, o[kVec - E + e], 1);
-                w[s < TS ? s : 0][PH][E + kVec + e] = __shfl_down_sync(0xffffffffu, o[e], 1);
+                w[s < TS ? s : 0][PH][e] = __shfl_up_sync(0xffffffffu, o[C - E + e], 1);
+                w[s < TS ? s : 0][PH][E + C + e] = __shfl_down_sync(0xffffffffu, o[e], 1);
             }
-        } else if (n >= t.n_first) {
+        } else if (n >= t.n_first && n < t.n_end) {
             real* dst = t.out + (t.y_out0 + n) * t.N + t.x_first;
-            if (t.v_lo <= 0 && t.v_hi >= kVec) {
-                stg_vec(dst, o);
+            if (t.v_lo <= 0 && t.v_hi >= C) {
+#pragma unroll
+                for (int j = 0; j < VT; ++j) {
+                    real ov[kVec];
+#pragma unroll
+                    for (int v = 0; v < kVec; ++v) ov[v] = o[j * kVec + v];
+                    stg_vec(dst + j * kVec, ov);
+                }
             } else {
 #pragma unroll
-                for (int v = 0; v < kVec; ++v)
+                for (int v = 0; v < C; ++v)
                     if (v >= t.v_lo && v < t.v_hi) dst[v] = o[v];
             }
         }
     }
     // ---- level 0: this thread's vector plus E halo columns each side, from the staged row ----
     {
-        const real* own = srow + E0 + t.lane * kVec;
-        real tmp[kVec];
-        lds_vec(tmp, own);
+        const real* own = srow + E0 + t.lane * C;
 #pragma unroll
-        for (int v = 0; v < kVec; ++v) w[0][PH][E + v] = tmp[v];
+        for (int j = 0; j < VT; ++j) {
+            real tmp[kVec];
+            lds_vec(tmp, own + j * kVec);
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) w[0][PH][E + j * kVec + v] = tmp[v];
+        }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             w[0][PH][e] = own[e - E];
-            w[0][PH][E + kVec + e] = own[kVec + e];
+            w[0][PH][E + C + e] = own[C + e];
         }
     }
 }
@@ -137,7 +151,6 @@ struct Stream {
 // time level, hand the stage back to the TMA unit if it was the stage's last row.
 template <int PH>
 __device__ __forceinline__ bool iteration(real (&w)[TS][R2][VW], const Stream& st, const Tile& t, int n) {
-    if (n >= st.NIT) return true;   // warp-uniform
     const int rr = n & (RB - 1);
     const int c = n / RB;
     const int s = c & (ST - 1);
@@ -193,14 +206,18 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const int X0 = (H / kVec) * kVec + xs * WU - HW;   // column of lane 0, element 0
     const drs_i64 ya = p.slow_lo + (drs_i64)yc * p.chunk;
     const drs_i64 yb = (ya + p.chunk < p.slow_hi) ? ya + p.chunk : p.slow_hi;
-    st.NIT = (int)(yb - ya) + TS * R2;   // + pipeline depth: one window height per level
+    // iterations: chunk rows + pipeline depth (one window height per level), rounded up to whole
+    // window rotations so that the unrolled phases need no guard; the surplus iterations stream
+    // rows past the chunk (or zero fill) and store nothing
+    const int n_end = (int)(yb - ya) + TS * R2;
+    st.NIT = (n_end + R2 - 1) / R2 * R2;
     st.NCH = (st.NIT + RB - 1) / RB;
     st.yrow0 = (int)(ya - TS * RJ);
     st.x_box = X0 - E0;
 
     Tile t;
     t.lane = lane;
-    t.x_first = X0 + lane * kVec;
+    t.x_first = X0 + lane * C;
     {
         const drs_i64 lo = (H > X0 + HW) ? H : X0 + HW;
         const drs_i64 hi = (p.N - H < X0 + HW + WU) ? p.N - H : X0 + HW + WU;
@@ -208,6 +225,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         t.v_hi = (int)(hi - t.x_first);
     }
     t.n_first = TS * R2;
+    t.n_end = n_end;
     t.y_out0 = ya - TS * R2;
     t.N = p.N;
     t.out = p.out;

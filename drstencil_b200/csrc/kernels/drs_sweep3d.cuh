@@ -50,7 +50,7 @@ struct Tile {
     int y_first;               // global row of tile row 0
     int ny;                    // storable tile rows: rows [0, ny) (rows below the tile start are always interior)
     drs_i64 z_out0;            // output plane produced at iteration 0
-    int n_first;
+    int n_first, n_end;        // iterations whose output plane lies inside the chunk
     drs_i64 M, N;
     real* out;
     // slab mode
@@ -78,7 +78,6 @@ struct Stream {
 
 template <int PH>
 __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream& st, const Tile& t, int n) {
-    if (n >= st.NIT) return true;   // warp-uniform
     if (!mbar_wait(&st.bars[n & (ST - 1)], (drs_u32)((n / ST) & 1), st.fault)) return false;
     // newest plane: own vectors of every tile row into the queue
     {
@@ -86,7 +85,7 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
 #pragma unroll
         for (int y = 0; y < RY; ++y) lds_vec(q[PH][y], pl + y * WB);
     }
-    if (n >= t.n_first) {
+    if (n >= t.n_first && n < t.n_end) {
         // staged planes of the window: sp[dk + RK] -> this thread's element 0 of tile row 0
         const real* sp[K2];
 #pragma unroll
@@ -184,7 +183,8 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const int Y0 = H + ys * RY;
     const drs_i64 za = p.slow_lo + (drs_i64)zc * p.chunk;
     const drs_i64 zb = (za + p.chunk < p.slow_hi) ? za + p.chunk : p.slow_hi;
-    st.NIT = (int)(zb - za) + 2 * RK;
+    const int n_end = (int)(zb - za) + 2 * RK;
+    st.NIT = (n_end + K2 - 1) / K2 * K2;   // whole queue rotations: the unrolled phases need no guard
     st.z0 = (int)(za - RK);
     st.x_box = X0 - E0;
     st.y_box = Y0 - RJ;
@@ -204,6 +204,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         t.ny = rows < RY ? (int)rows : RY;
     }
     t.n_first = 2 * RK;
+    t.n_end = n_end;
     t.z_out0 = za - 2 * RK;
     t.M = p.M;
     t.N = p.N;

@@ -124,6 +124,8 @@ def test_fp32_temporal_within_1e5(built):
     ("2d5pt_star", dict(sn=7)), ("2d5pt_star", dict(sn=1000, stages=2, rows_per_stage=1)),
     ("2d9pt_box", dict(step=3, sn=16, warps=4, stages=8, rows_per_stage=8)),
     ("2d25pt_box", dict(streaming=1, bx=128, sn=33, prefetch=1)),
+    ("2d5pt_star", dict(block_merge_x=2, sn=50)), ("2d9pt_box", dict(step=4, vectors=2, sn=40)),
+    ("2d9pt_star", dict(step=2, vectors=2)), ("2d25pt_box", dict(vectors=2, sn=19)),
     ("3d7pt_star", dict(sn=5, rows_3d=4)), ("3d7pt_star", dict(sn=64, rows_3d=16, warps=1, stages=8)),
     ("3d9pt_cross", dict(bx=32, by=4, sn=9)),
 ])
