@@ -100,6 +100,8 @@ def lib():
         "drs_plan_set_peers": (i32, [vp, P(vp), P(vp), P(vp), ll, ll]),
         "drs_device_malloc": (i32, [ctypes.c_size_t, P(vp)]),
         "drs_device_free": (i32, [vp]),
+        "drs_device_upload": (i32, [vp, vp, ctypes.c_size_t]),
+        "drs_device_download": (i32, [vp, vp, ctypes.c_size_t]),
         "drs_ipc_export": (i32, [vp, ctypes.c_char_p]),
         "drs_ipc_import": (i32, [ctypes.c_char_p, P(vp)]),
         "drs_ipc_close": (i32, [vp]),

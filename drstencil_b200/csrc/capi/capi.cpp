@@ -740,6 +740,16 @@ int drs_device_malloc(size_t bytes, void** d_ptr) {
     return DRS_OK;
 }
 int drs_device_free(void* d_ptr) { cudaFree(d_ptr); return DRS_OK; }
+int drs_device_upload(void* d_dst, const void* h_src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaMemcpy H2D: ") + cudaGetErrorString(e));
+    return DRS_OK;
+}
+int drs_device_download(void* h_dst, const void* d_src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaMemcpy D2H: ") + cudaGetErrorString(e));
+    return DRS_OK;
+}
 
 // ---- emitters ----------------------------------------------------------------------------
 int drs_emit_program(const drs_stencil* s, const drs_knobs* k, const char* kernel_name, const char* path) {

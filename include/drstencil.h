@@ -163,6 +163,8 @@ int drs_plan_set_peers(drs_plan *p, void *const my_bases[2], void *const lower_b
  * exported must come from drs_device_malloc (a whole cudaMalloc allocation). */
 int drs_device_malloc(size_t bytes, void **d_ptr);
 int drs_device_free(void *d_ptr);
+int drs_device_upload(void *d_dst, const void *h_src, size_t bytes);   /* blocking cudaMemcpy H2D */
+int drs_device_download(void *h_dst, const void *d_src, size_t bytes); /* blocking cudaMemcpy D2H */
 int drs_ipc_export(void *d_ptr, unsigned char handle[64]);
 int drs_ipc_import(const unsigned char handle[64], void **d_ptr);
 int drs_ipc_close(void *d_ptr);
