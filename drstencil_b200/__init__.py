@@ -98,6 +98,8 @@ def lib():
         "drs_plan_launch_count": (ll, [vp]),
         "drs_plan_set_slab": (i32, [vp, ll, ll, ll]),
         "drs_plan_set_peers": (i32, [vp, P(vp), P(vp), P(vp), ll, ll]),
+        "drs_signal_peers": (i32, [vp, vp, vp, ll, vp]),
+        "drs_wait_flags": (i32, [vp, vp, i32, i32, ll, vp]),
         "drs_device_malloc": (i32, [ctypes.c_size_t, P(vp)]),
         "drs_device_free": (i32, [vp]),
         "drs_device_upload": (i32, [vp, vp, ctypes.c_size_t]),
@@ -426,6 +428,12 @@ class Plan:
     def set_peers(self, my_bases, lower_bases, upper_bases, lower_lo: int, upper_lo: int) -> None:
         arr = lambda xs: (ctypes.c_void_p * 2)(*[_ptr(x) or None for x in xs])
         _check(lib().drs_plan_set_peers(self._h, arr(my_bases), arr(lower_bases), arr(upper_bases), lower_lo, upper_lo))
+
+    def signal_peers(self, lower_flag: int, upper_flag: int, value: int, stream=None) -> None:
+        _check(lib().drs_signal_peers(self._h, lower_flag or None, upper_flag or None, value, _stream(stream)))
+
+    def wait_flags(self, my_flags: int, wait_lower: bool, wait_upper: bool, value: int, stream=None) -> None:
+        _check(lib().drs_wait_flags(self._h, my_flags, int(wait_lower), int(wait_upper), value, _stream(stream)))
 
     def emit_program(self, path: str, kernel_name: Optional[str] = None) -> None:
         ck = self.knobs.to_c()

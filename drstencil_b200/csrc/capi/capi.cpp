@@ -244,7 +244,7 @@ struct drs_plan {
     bool loaded = false;
     int device = -1;
     CUmodule mod = nullptr;
-    CUfunction f_sweep = nullptr, f_gold = nullptr, f_check = nullptr;
+    CUfunction f_sweep = nullptr, f_gold = nullptr, f_check = nullptr, f_signal = nullptr, f_wait = nullptr;
     int regs = 0, spill = 0;
     int* d_fault = nullptr;
     double* d_res = nullptr;
@@ -291,6 +291,9 @@ int ensure_loaded(drs_plan* p) {
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(gold_): " + cu_err(r));
     r = d.ModuleGetFunction(&p->f_check, p->mod, ("check_" + nm).c_str());
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(check_): " + cu_err(r));
+    r = d.ModuleGetFunction(&p->f_signal, p->mod, ("signal_" + nm).c_str());
+    if (r == CUDA_SUCCESS) r = d.ModuleGetFunction(&p->f_wait, p->mod, ("wait_" + nm).c_str());
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(signal_/wait_): " + cu_err(r));
     if (cudaMalloc(&p->d_fault, sizeof(int)) != cudaSuccess) return fail(DRS_E_CUDA, "cudaMalloc(fault flag)");
     cudaMemset(p->d_fault, 0, sizeof(int));
     if (cudaMalloc(&p->d_res, 2 * sizeof(double)) != cudaSuccess) return fail(DRS_E_CUDA, "cudaMalloc(result)");
@@ -634,7 +637,8 @@ int drs_plan_sync_check(drs_plan* p, void* stream) {
     if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("fault flag read: ") + cudaGetErrorString(e));
     if (f) {
         cudaMemset(p->d_fault, 0, sizeof(int));
-        return fail(DRS_E_KERNEL, "sweep kernel pipeline watchdog fired (a TMA stage never arrived)");
+        return fail(DRS_E_KERNEL, f == 2 ? "slab step flag never arrived from a neighbour GPU (5 s watchdog)"
+                                         : "sweep kernel pipeline watchdog fired (a TMA stage never arrived)");
     }
     return DRS_OK;
 }
@@ -711,6 +715,28 @@ int drs_plan_set_peers(drs_plan* p, void* const my_bases[2], void* const lower_b
         p->upper_bases[b] = upper_bases ? upper_bases[b] : nullptr;
     }
     p->lower_lo = lower_lo; p->upper_lo = upper_lo;
+    return DRS_OK;
+}
+
+int drs_signal_peers(drs_plan* p, void* lower_flag, void* upper_flag, long long value, void* stream) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    void* args[] = {&lower_flag, &upper_flag, &value};
+    CUresult r = driver().LaunchKernel(p->f_signal, 1, 1, 1, 32, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch signal_: " + cu_err(r));
+    p->launches++;
+    return DRS_OK;
+}
+
+int drs_wait_flags(drs_plan* p, const void* my_flags, int wait_lower, int wait_upper, long long value, void* stream) {
+    if (!p || !my_flags) return fail(DRS_E_ARG, "null argument");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    void* args[] = {(void*)&my_flags, &wait_lower, &wait_upper, &value, &p->d_fault};
+    CUresult r = driver().LaunchKernel(p->f_wait, 1, 1, 1, 32, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch wait_: " + cu_err(r));
+    p->launches++;
     return DRS_OK;
 }
 

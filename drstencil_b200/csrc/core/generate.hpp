@@ -185,6 +185,8 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_NAME dr_" << s.name << "\n";
     o << "#define DRS_GOLD_NAME gold_" << s.name << "\n";
     o << "#define DRS_CHECK_NAME check_" << s.name << "\n";
+    o << "#define DRS_SIGNAL_NAME signal_" << s.name << "\n";
+    o << "#define DRS_WAIT_NAME wait_" << s.name << "\n";
     o << "#define DRS_HALO " << s.halo << "\n";
     o << "#define DRS_TS " << s.ts << "\n";
     o << "#define DRS_RK " << s.rk << "\n#define DRS_RJ " << s.rj << "\n#define DRS_E " << s.e << "\n";

@@ -66,3 +66,35 @@ DRS_CHECK_NAME(const __grid_constant__ drs::Params p, const drs::real* __restric
         atomicAdd(res + 1, sq);
     }
 }
+
+// ---- cross-GPU step flags for slab runs (one process per GPU, buffers mapped with CUDA IPC) ----
+// After sweep s a rank stores s+1 into a slot of each neighbour's flag array (system-scope
+// release, after a system fence that orders the sweep's peer stores before it); before sweep s+1
+// it waits until both of its own slots hold >= s+1.  Ranks run on different GPUs, so the waiting
+// kernel never shares a device with the kernel it waits for.
+extern "C" __global__ void DRS_SIGNAL_NAME(long long* peer_a, long long* peer_b, long long value) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        if (peer_a) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_a), "l"(value) : "memory");
+        if (peer_b) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer_b), "l"(value) : "memory");
+    }
+}
+
+extern "C" __global__ void DRS_WAIT_NAME(const long long* mine, int use_a, int use_b, long long value, int* fault) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const drs_u64 t0 = drs::global_ns();
+        for (int slot = 0; slot < 2; ++slot) {
+            if (!(slot == 0 ? use_a : use_b)) continue;
+            for (;;) {
+                long long v;
+                asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(mine + slot) : "memory");
+                if (v >= value) break;
+                if (drs::global_ns() - t0 > 5000000000ull) {   // 5 s: a neighbour died
+                    if (fault) atomicExch(fault, 2);
+                    return;
+                }
+                __nanosleep(200);
+            }
+        }
+    }
+}

@@ -159,6 +159,13 @@ int drs_plan_set_slab(drs_plan *p, long long global_slow, long long lo, long lon
  * owned global planes (their `lo`). */
 int drs_plan_set_peers(drs_plan *p, void *const my_bases[2], void *const lower_bases[2],
                        void *const upper_bases[2], long long lower_lo, long long upper_lo);
+/* Cross-GPU step flags.  Each rank owns a device array of two 64-bit slots (slot 0 written by its
+ * lower neighbour, slot 1 by its upper neighbour), exported with drs_ipc_export.  drs_signal_peers
+ * enqueues, after the work already on `stream`, a system-scope release store of `value` into the
+ * lower neighbour's slot 1 (`lower_flag` = that address) and the upper neighbour's slot 0;
+ * drs_wait_flags enqueues a wait until the selected slots of `my_flags` hold >= value. */
+int drs_signal_peers(drs_plan *p, void *lower_flag, void *upper_flag, long long value, void *stream);
+int drs_wait_flags(drs_plan *p, const void *my_flags, int wait_lower, int wait_upper, long long value, void *stream);
 /* CUDA IPC plumbing so that one process per GPU can map a neighbour's buffer.  Buffers to be
  * exported must come from drs_device_malloc (a whole cudaMalloc allocation). */
 int drs_device_malloc(size_t bytes, void **d_ptr);
