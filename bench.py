@@ -7,10 +7,13 @@ Metric (BASELINE.json): GStencil/s and achieved HBM GB/s (% of roofline) per ste
 A "step" is one run of the reference's emitted host loop (codegen_2d.hpp:610-613) over one
 synthetic grid: `for (t = 0; t < iterations; t += 2*step) { sweep(A,B); sweep(B,A); }`.
 
-  N = 1   workload c2 (BASELINE.json configs[1]): 2d9pt_box fp64 16384^2, temporal depth 4,
-          128 timesteps per step; the other single-GPU configs are reported in `per_config`.
-  N > 1   workload c5: 3d7pt_star fp64 1536^3 slab-decomposed along k over N GPUs with the
-          fused NVLink halo push, 100 timesteps per step (strong scaling: the grid is fixed).
+  Workload, every N: c5 = 3d7pt_star fp64 1536^3, 100 timesteps per step -- the one BASELINE.json
+          configuration defined at 1/2/4/8 GPUs (it fits one B200: 2 x 27 GiB), so that the per-N
+          values form one strong-scaling series.  N = 1 sweeps the whole grid on one GPU; N > 1
+          slab-decomposes it along k with the fused NVLink halo push.
+  N = 1   additionally reports every other configuration (c1-c4) in `per_config`, each with its
+          own roofline fraction -- c2 (2d9pt_box fp64 16384^2, temporal depth 4) is the
+          temporally fused one -- and the CPU baseline.
 
 `value`     device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
 `e2e`       the same step through the host-buffer C-ABI call drs_run_host (pinned host memory:
@@ -201,7 +204,7 @@ def run_single(args, rank, world):
     import torch
     import drstencil_b200 as drs
     from drstencil_b200.presets import PRESETS
-    wl = args.workload or "c2"
+    wl = args.workload or "c5"
     preset, timesteps, desc = WORKLOADS[wl]
     path, kn = PRESETS[preset]
     st = drs.Stencil.from_file(path)
@@ -213,7 +216,7 @@ def run_single(args, rank, world):
     g = torch.Generator(device="cuda").manual_seed(rank)
     A = torch.rand(shape, dtype=dtype, device="cuda", generator=g)
     if dtype == torch.float64:
-        A.mul_(1e-140)   # sum of coefficients > 1: keeps (K + W) * timesteps updates inside fp64 range
+        A.mul_(1e-200)   # sum of coefficients > 1: keeps (K + W) * timesteps updates inside fp64 range
     B = torch.zeros_like(A)
     sampler = ClockSampler(torch.cuda.current_device())
     if world > 1:
@@ -241,7 +244,8 @@ def run_single(args, rank, world):
     line = {
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if kn.dtype == drs.F32 else "f64", "data": "synthetic",
+        "scaling": "strong" if wl == "c5" else "weak", "vs_baseline": None,
+        "dtype": "f32" if kn.dtype == drs.F32 else "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (wl, desc), "grid": list(shape), "timesteps_per_step": timesteps,
                    "sweeps_per_step": sweeps_per_step, "temporal_depth": kn.step, "kernel": info.kernel_name,
                    "tile": {"warps_per_cta": info.warps_per_cta, "tile_x": info.tile_x, "chunk": info.chunk,
@@ -257,16 +261,20 @@ def run_single(args, rank, world):
     }
     # ---- e2e: the host-buffer entry point (H2D + schedule + D2H in the timed region) ----
     if rank == 0 or world > 1:
-        hA = torch.rand(shape, dtype=dtype).pin_memory()
-        hB = torch.zeros(shape, dtype=dtype).pin_memory()
-        e2e_steps = max(2, min(args.steps, 5))
-        plan.run_host(hA, hB, timesteps)               # warm (allocates the device pair)
-        t0 = time.perf_counter()
+        del A, B
+        torch.cuda.empty_cache()
+        pinned = True
+        try:
+            hA = torch.empty(shape, dtype=dtype, pin_memory=True)
+        except RuntimeError:
+            pinned = False
+            hA = torch.empty(shape, dtype=dtype)
+        hA.fill_(0.5e-100)
+        e2e_steps = 2 if all_points(shape) * esize > 8 * 2 ** 30 else max(2, min(args.steps, 5))
+        plan.run_host(hA, None, timesteps)               # warm (allocates the device pair)
         dev_ms = 0.0
         for _ in range(e2e_steps):
-            dev_ms += plan.run_host(hA, hB, timesteps)
-            hA.mul_(0).add_(0.5)                       # fresh finite input for the next step (host side, untimed below)
-        wall = time.perf_counter() - t0
+            dev_ms += plan.run_host(hA, None, timesteps)
         e_secs = dev_ms * 1e-3
         if world > 1:
             import torch.distributed as dist
@@ -275,9 +283,11 @@ def run_single(args, rank, world):
             e_secs = float(t)
         nbytes = all_points(shape) * esize
         line["e2e"] = {"value": world * upd * e2e_steps / e_secs / 1e9, "unit": "GStencil/s",
-                       "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
-                       "ms_per_step": e_secs / e2e_steps * 1e3, "api": "drs_run_host (C ABI, pinned host buffers)"}
-        del hA, hB
+                       "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+                       "ms_per_step": e_secs / e2e_steps * 1e3,
+                       "api": "drs_run_host (C ABI): %s host grid -> H2D, zeroed second buffer, schedule, D2H of the result"
+                              % ("pinned" if pinned else "pageable")}
+        del hA
     return line, plan
 
 
@@ -288,7 +298,7 @@ def per_config(args):
     from drstencil_b200.presets import PRESETS
     peak, _ = measured_peak()
     out = []
-    for wl in ("c1", "c3", "c4", "c5"):
+    for wl in ("c1", "c2", "c3", "c4"):
         preset, timesteps, desc = WORKLOADS[wl]
         path, kn = PRESETS[preset]
         st = drs.Stencil.from_file(path)
@@ -301,15 +311,20 @@ def per_config(args):
             dtype = torch.float32 if kn.dtype == drs.F32 else torch.float64
             A = torch.rand(shape, dtype=dtype, device="cuda")
             B = torch.zeros_like(A)
-            ts = timesteps if wl != "c5" else 10
+            ts = timesteps if wl != "c2" else 32
             k = 5 if wl == "c1" else 2
+            if dtype == torch.float64:
+                A.mul_(1e-100)
             secs, launches = time_steps(plan, A, B, ts, k, 2)
             info = plan.info
             upd = interior_points(shape, info.halo) * drs.sweep_count(ts, kn.step) * kn.step * k
             ach = all_points(shape) * 2 * esize / (secs / launches) / 1e9
             out.append({"workload": "%s: %s" % (wl, desc), "value": upd / secs / 1e9, "unit": "GStencil/s",
-                        "kernel": info.kernel_name, "launch_ms": secs / launches * 1e3, "gpu_launches": launches,
-                        "roofline_frac": ach / peak, "achieved_gbs": ach, "n_gpus": 1})
+                        "temporal_depth": kn.step, "kernel": info.kernel_name, "launch_ms": secs / launches * 1e3,
+                        "gpu_launches": launches, "n_gpus": 1,
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                     "gstencil_roofline": peak / (2 * esize) * kn.step,
+                                     "frac_of_single_step_gstencil_roofline": (upd / secs / 1e9) / (peak / (2 * esize))}})
             del A, B, plan
             torch.cuda.empty_cache()
         except Exception as e:
@@ -322,7 +337,7 @@ def run_reference(args, rank):
     is not a CPU implementation), all host threads, bounded sample per step."""
     if rank != 0:
         return None
-    wl = args.workload or ("c2" if args.gpus == 1 else "c5")
+    wl = args.workload or "c5"
     vals = []
     base = None
     for i in range(args.warmup + args.steps):
@@ -370,7 +385,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if world > 1 and (args.workload in (None, "c5")):
+    if world > 1 and (args.workload in (None, "c5")):   # world == 1 sweeps the whole grid on one GPU
         from drstencil_b200 import slab
         line = slab.bench_slab(args, rank, world, WORKLOADS["c5"], measured_peak())
     else:
@@ -378,10 +393,9 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_extras:
             line["per_config"] = per_config(args)
-            line["cpu_baseline"] = cpu_baseline(args.workload or "c2")
-            ref = reference_gpu_kernel(args.workload or "c2")
-            if ref:
-                line["reference_gpu_kernel"] = ref
+            line["cpu_baseline"] = cpu_baseline(args.workload or "c5")
+            refs = {w: reference_gpu_kernel(w) for w in ("c1", "c2", "c4")}
+            line["reference_gpu_kernels"] = {w: r for w, r in refs.items() if r}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist

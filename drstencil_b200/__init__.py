@@ -407,7 +407,7 @@ class Plan:
     def run_host(self, h_a, h_b, iterations: int) -> float:
         """The emitted main()'s data path on host arrays (H2D, schedule, D2H of A); returns device ms."""
         ms = ctypes.c_float()
-        _check(lib().drs_run_host(self._h, _ptr(h_a), _ptr(h_b), iterations, ctypes.byref(ms)))
+        _check(lib().drs_run_host(self._h, _ptr(h_a), _ptr(h_b) or None, iterations, ctypes.byref(ms)))
         return ms.value
 
     def check_error(self, d_out, d_ref):

@@ -1,0 +1,179 @@
+"""Search space, validity filter and configuration names.
+
+Reference: benchmarks/2d5pt_star/tuning.py:13-86,124-139 (2D) and benchmarks/3d7pt_star/tuning.py
+(3D).  A configuration is the reference's tuple
+  (step, dist, (bx, by), streaming, sn, s_unroll, blockMergeX, mx, blockMergeY, my, merge_forward, prefetch)
+extended by the engine's own axes (ring stages, warps per CTA, launch-bounds blocks, vectors per
+thread, rows per thread in 3D).
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field, replace
+from typing import Iterator, List
+
+from .. import Knobs
+
+
+@dataclass(frozen=True)
+class Config:
+    step: int = 1
+    dist: int = 0
+    bx: int = 64
+    by: int = 1
+    streaming: bool = True
+    sn: int = 128
+    s_unroll: int = 4
+    block_merge_x: bool = True
+    mx: int = 1
+    block_merge_y: bool = False
+    my: int = 1
+    merge_forward: int = 5
+    prefetch: bool = False
+    # engine axes
+    stages: int = 4
+    min_blocks: int = 0
+    rows_3d: int = 0
+    dtype: str = "f64"
+    fuse: str = "temporal"
+
+    def knobs(self) -> Knobs:
+        k = Knobs(step=self.step, sn=self.sn, bx=self.bx, by=self.by, streaming=int(self.streaming),
+                  stream_unroll=self.s_unroll, merge_forward=self.merge_forward, dtype=self.dtype, fuse=self.fuse)
+        if self.dist:
+            k.set("dist", self.dist)
+        if self.block_merge_x:
+            k.set("block_merge_x", self.mx)
+        else:
+            k.set("cyclic_merge_x", self.mx)
+        if self.block_merge_y:
+            k.set("block_merge_y", self.my)
+        else:
+            k.set("cyclic_merge_y", self.my)
+        if self.prefetch:
+            k.set("prefetch", 1)
+        k.set("stages", self.stages)
+        if self.min_blocks:
+            k.set("min_blocks", self.min_blocks)
+        if self.rows_3d:
+            k.set("rows_3d", self.rows_3d)
+        return k
+
+
+def cfg_to_string(c: Config) -> str:
+    """The reference's result-file name grammar (tuning.py:72-86):
+    fu{step}d{dist}bx{bx}[y{by}]sn{sn}u{unroll}(bmx|cmx){m}[(bmy|cmy){m}]mf{t}[p], followed by the
+    engine-only axes when they differ from the defaults: st{stages} mb{min_blocks} ry{rows} and the
+    dtype/fuse tags."""
+    if c.streaming:
+        s = "fu%dd%dbx%dsn%du%d" % (c.step, c.dist, c.bx, c.sn, c.s_unroll)
+    else:
+        s = "fu%dd%dbx%dy%d" % (c.step, c.dist, c.bx, c.by)
+    s += ("bmx" if c.block_merge_x else "cmx") + str(c.mx)
+    if not c.streaming:
+        s += ("bmy" if c.block_merge_y else "cmy") + str(c.my)
+    s += "mf%d" % c.merge_forward
+    if c.prefetch and c.streaming:
+        s += "p"
+    if c.stages != 4:
+        s += "st%d" % c.stages
+    if c.min_blocks:
+        s += "mb%d" % c.min_blocks
+    if c.rows_3d:
+        s += "ry%d" % c.rows_3d
+    if c.dtype != "f64":
+        s += c.dtype
+    if c.fuse != "temporal":
+        s += "alg"
+    return s
+
+
+def cfg_to_command_line(c: Config) -> str:
+    """Arguments for the `drstencil` CLI that reproduce this configuration (tuning.py:50-69)."""
+    cmd = " --step %d --dist %d --bx %d" % (c.step, c.dist, c.bx)
+    if c.streaming:
+        cmd += " --streaming --sn %d --stream-unroll %d" % (c.sn, c.s_unroll)
+    else:
+        cmd += " --by %d" % c.by
+    cmd += (" --block-merge-y %d" if c.block_merge_y else " --cyclic-merge-y %d") % c.my
+    cmd += (" --block-merge-x %d" if c.block_merge_x else " --cyclic-merge-x %d") % c.mx
+    cmd += " --merge-forward %d" % c.merge_forward
+    if c.prefetch and c.streaming:
+        cmd += " --prefetch"
+    if c.stages != 4:
+        cmd += " --stages %d" % c.stages
+    if c.min_blocks:
+        cmd += " --min-blocks %d" % c.min_blocks
+    if c.rows_3d:
+        cmd += " --rows-3d %d" % c.rows_3d
+    if c.dtype != "f64":
+        cmd += " --dtype " + c.dtype
+    if c.fuse != "temporal":
+        cmd += " --fuse algebraic"
+    return cmd
+
+
+def filter_config(c: Config, dim: int, radius: int, esize: int = 8) -> bool:
+    """Validity and pruning.  The reference rejects tiles that do not cover the halo and shared
+    memory above 32 KiB (tuning.py:13-47); here the limits are the B200's (227 KiB per CTA, 64
+    warps and 64K registers per SM) plus a resource model that drops configurations which cannot
+    keep enough bytes in flight to cover HBM latency."""
+    vec = 16 // esize
+    warps = max(1, (c.bx if (dim == 2 and c.streaming) else c.bx * c.by) // 32)
+    if warps > 16 or (c.bx * max(1, c.by)) % 32:
+        return False
+    if c.stages not in (2, 4, 8) or c.s_unroll not in (1, 2, 4, 8, 16):
+        return False
+    if dim == 2:
+        vt = min(2, c.mx) if c.block_merge_x else 1
+        cols = vt * vec
+        e = radius
+        hw = ((c.step - 1) * e + vec - 1) // vec * vec if c.fuse == "temporal" else 0
+        if 32 * cols - 2 * hw < vec:                       # not covering the halo region
+            return False
+        wb = 32 * cols + 2 * ((e + vec - 1) // vec * vec)
+        if wb > 256:
+            return False
+        stage = (c.s_unroll * wb * esize + 127) // 128 * 128
+        smem = warps * c.stages * (stage + 8)
+        live = (c.step if c.fuse == "temporal" else 1) * (2 * radius + 1) * (cols + 2 * e) * (esize // 4)
+    else:
+        ry = c.rows_3d or 8
+        wb = 32 * vec + 2 * ((radius + vec - 1) // vec * vec)
+        stage = (wb * (ry + 2 * radius) * esize + 127) // 128 * 128
+        if c.stages < 2 * radius + 2:
+            return False
+        smem = warps * c.stages * (stage + 8)
+        live = (2 * radius + 1) * ry * vec * (esize // 4)
+    if smem > 227 * 1024:
+        return False
+    if live + 40 > 255:                                     # the window cannot live in registers
+        return False
+    # bytes a resident SM keeps in flight: must cover ~44 KB (6.5 TB/s x ~1 us / 148 SMs)
+    regs = min(255, live + 56)
+    ctas = min(32, 227 * 1024 // max(smem, 1), 65536 // (regs * warps * 32))
+    if c.min_blocks and c.min_blocks > ctas:
+        return False
+    in_flight = ctas * warps * (c.stages - 1 if dim == 2 else c.stages - 2 * radius) * stage
+    return ctas >= 1 and in_flight >= 24 * 1024
+
+
+def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse: str = "temporal") -> List[Config]:
+    """Cartesian product of the axes (reference: tuning.py:124-139), filtered."""
+    esize = 8 if dtype == "f64" else 4
+    out = []
+    if dim == 2:
+        for bx, sn, unroll, mx, stages, mb in itertools.product(
+                (32, 64, 128), (32, 64, 128, 256, 512), (2, 4, 8), (1, 2), (2, 4), (0, 4)):
+            c = Config(step=step, bx=bx, by=1, streaming=True, sn=sn, s_unroll=unroll, block_merge_x=True, mx=mx,
+                       stages=stages, min_blocks=mb, dtype=dtype, fuse=fuse)
+            if filter_config(c, 2, radius, esize):
+                out.append(c)
+    else:
+        for (bx, by), sn, my, stages in itertools.product(
+                ((32, 1), (32, 2), (32, 4)), (8, 16, 32, 64), (1, 2), (4, 8)):
+            c = Config(step=step, bx=bx, by=by, streaming=False, sn=sn, block_merge_y=True, my=my, rows_3d=4 * my,
+                       stages=stages, dtype=dtype, fuse=fuse)
+            if filter_config(c, 3, radius * (step if fuse == "algebraic" or dim == 3 else 1), esize):
+                out.append(c)
+    return out

@@ -134,7 +134,9 @@ int drs_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int
 /* same schedule with the gold kernel (codegen_2d.hpp:638-642) */
 int drs_gold_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int *sweeps);
 /* the whole emitted main() data path on HOST buffers (codegen_2d.hpp:572-583,604-619,647):
- * H2D of a and b, the schedule, D2H of a.  h_a/h_b hold L*M*N elements of the plan's dtype. */
+ * H2D of a and b, the schedule, D2H of a.  h_a/h_b hold L*M*N elements of the plan's dtype;
+ * h_b == NULL stands for the all-zero second buffer the reference always uses (common.hpp:34-45)
+ * and is cleared on the device instead of being copied. */
 int drs_run_host(drs_plan *p, void *h_a, void *h_b, int iterations, float *device_ms);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */

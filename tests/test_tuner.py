@@ -1,0 +1,58 @@
+"""Tuner rebuild: configuration-name grammar (reference tuning.py:72-86), search-space filter and
+the name-keyed Nsight Compute parser, on CSV captured from Nsight Compute 2025.2 on the B200 box
+(tests/golden/ncu_*_sample.csv).  CPU only."""
+import os
+
+from helpers import ROOT
+
+
+def test_config_name_grammar_matches_reference():
+    from drstencil_b200.tuner.space import Config, cfg_to_command_line, cfg_to_string
+    # streaming: fu{step}d{dist}bx{bx}sn{sn}u{unroll}(bmx|cmx){m}mf{t}[p]
+    c = Config(step=2, dist=2, bx=128, streaming=True, sn=64, s_unroll=4, block_merge_x=False, mx=2, prefetch=True)
+    assert cfg_to_string(c) == "fu2d2bx128sn64u4cmx2mf5p"
+    assert cfg_to_command_line(c) == (" --step 2 --dist 2 --bx 128 --streaming --sn 64 --stream-unroll 4"
+                                      " --cyclic-merge-y 1 --cyclic-merge-x 2 --merge-forward 5 --prefetch")
+    # non-streaming: fu..d..bx..y..(bmx|cmx)m(bmy|cmy)m mf
+    c = Config(step=1, dist=1, bx=32, by=8, streaming=False, block_merge_x=True, mx=2, block_merge_y=False, my=4)
+    assert cfg_to_string(c) == "fu1d1bx32y8bmx2cmy4mf5"
+    # engine axes are appended only when they differ from the defaults
+    c = Config(step=4, bx=64, sn=256, mx=2, stages=8, min_blocks=4, dtype="f32", fuse="algebraic")
+    assert cfg_to_string(c) == "fu4d0bx64sn256u4bmx2mf5st8mb4f32alg"
+
+
+def test_search_space_filter():
+    from drstencil_b200.tuner.space import Config, filter_config, search_space
+    sp = search_space(2, 1, step=4)
+    assert 50 < len(sp) < 2000
+    assert all(filter_config(c, 2, 1) for c in sp)
+    # tiles that do not cover the halo are dropped (reference tuning.py:27)
+    assert not filter_config(Config(step=40, bx=64, sn=64, mx=1), 2, 1)
+    # fp32 with two vectors per thread exceeds the 256-element TMA box
+    assert not filter_config(Config(step=1, bx=64, sn=64, mx=2, dtype="f32"), 2, 2, esize=4)
+    # 3D ring must hold the whole k window
+    assert not filter_config(Config(step=1, bx=32, by=2, streaming=False, stages=2, rows_3d=8), 3, 1)
+    assert search_space(3, 1)
+
+
+def test_knobs_roundtrip(built):
+    import drstencil_b200 as drs
+    from drstencil_b200.tuner.space import Config
+    c = Config(step=4, bx=64, sn=256, s_unroll=8, mx=2, stages=2, min_blocks=4)
+    st = drs.Stencil.from_file(os.path.join(ROOT, "stc", "2d9pt_box.stc")).set_size((1024, 1024))
+    info = drs.Plan(st, c.knobs()).info
+    assert (info.warps_per_cta, info.chunk, info.stages, info.rows_per_stage, info.tile_x) == (2, 256, 2, 8, 120)
+
+
+def test_ncu_parser_by_name():
+    from drstencil_b200.tuner import metrics
+    rows = metrics.parse(open(os.path.join(ROOT, "tests", "golden", "ncu_long_sample.csv")).read())
+    assert len(rows) == 5
+    dr = [r for r in rows if "dr_c2" in r["kernel"]]
+    assert len(dr) == 3 and all(1e-3 < r["gpu__time_duration.sum"] < 2e-3 for r in dr)   # seconds
+    raw = metrics.parse(open(os.path.join(ROOT, "tests", "golden", "ncu_raw_sample.csv")).read())
+    s = metrics.summarise(raw)
+    assert s["kernel"].startswith("dr_c2") and s["launches"] == 2
+    assert 4.2e9 < s["dram_bytes"] < 4.6e9                      # ~ the 4.29 GB algorithmic bytes
+    assert 3000 < s["dram_gbs"] < 3600
+    assert s["launch__registers_per_thread"] == 130
