@@ -9,6 +9,7 @@
 // with literal coefficients, the operator extents and the tile/pipeline constants.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <sstream>
 #include <string>
@@ -30,6 +31,13 @@ struct KernelSpec {
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
     int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
     bool tma_ok = true;         // false -> rows not 16-byte multiples: naive kernel does the sweep
+    // row-factorised evaluation (temporal mode only): out = sum_dj w[dj] * H(row j+dj) + residual terms,
+    // H(row)(x) = sum_di h[di] * u[row][x+di] computed once per row and reused by every output row
+    bool factored = false;
+    std::vector<double> fh;                 // h[di + e]
+    std::vector<double> fw;                 // w[dj + rj]
+    std::vector<Term> fres;                 // residual terms (coefficient = K - w*h where that is not zero)
+    int fops = 0;                           // arithmetic operations per output in factored form
     std::string name = "stencil";
     std::string note;           // why a requested mode was changed, for logs
 
@@ -52,6 +60,8 @@ inline int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 inline bool knob_given(const drs_knobs& k, int bit) { return (k.explicit_mask >> bit) & 1; }
 enum KnobBit { KB_STEP = 0, KB_DIST, KB_STREAMING, KB_BX, KB_BY, KB_SN, KB_UNROLL, KB_BMX, KB_BMY, KB_CMX, KB_CMY,
                KB_PREFETCH, KB_MERGE_FWD, KB_CHECK, KB_DTYPE, KB_FUSE };
+
+inline bool factorise_rows(KernelSpec& s);
 
 // Chooses the specialisation.  Returns "" or an error text (-> DRS_E_ARG).
 //
@@ -104,6 +114,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.rj = std::max(s.rj, std::abs(t.dj));
         s.e = std::max(s.e, std::abs(t.di));
     }
+    if (s.ts > 1 && k.reserved[6] == 0) factorise_rows(s);
     // --- geometry ---
     const long long slow = s.dim == 3 ? st.L : st.M;
     const long long slow_out = std::max<long long>(1, slow - 2 * s.halo);
@@ -138,8 +149,9 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     {
         // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
         // per SM is the most that budget allows (never forces spills)
-        const int live = s.dim == 2 ? s.ts * (2 * s.rj + 1) * (s.cols() + 2 * s.e) * (s.esize() / 4)
-                                    : (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4);
+        const int live = s.dim == 3 ? (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4)
+                         : s.ts == 1 ? (2 * s.rj + 1) * (s.cols() + 2 * s.e) * (s.esize() / 4)
+                                     : (s.ts * (2 * s.rj + 1) * s.cols() + 2 * (s.cols() + 2 * s.e)) * (s.esize() / 4);
         const int est = std::min(255, live + (s.dim == 2 ? 56 : 72));
         s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
     }
@@ -153,6 +165,121 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     // TMA needs 16-byte row pitch
     s.tma_ok = (st.N % vec) == 0;
     return "";
+}
+
+// Row factorisation of a 2D operator K[dj][di] (SURVEY.md hard part "fp64 compute ceiling"):
+// if the rows of K are multiples of one row vector h up to a few entries, then
+//     out(j, x) = sum_dj w[dj] * H(j + dj, x)  +  sum_residual r * u[j+dj][x+di],   H(row, x) = sum_di h[di] * u[row][x+di]
+// and H(row, .) is shared by all the output rows that touch `row`.  2d9pt_box (0.3 / 0.2 / 0.1):
+// h = (0.1, 0.2, 0.1), w = (1, 2, 1), one residual -0.1 at the centre -> 6 operations per output
+// instead of 9.  Exact in real arithmetic (w*h reproduces K bit for bit or leaves an explicit
+// residual), but it re-associates the sum, so it is used only where the result is held to a
+// tolerance (temporal depth > 1), never for the bit-exact single-step chain.
+inline bool factorise_rows(KernelSpec& s) {
+    if (s.dim != 2 || s.chain.size() < 6) return false;
+    const int RJ = s.rj, E = s.e, NR = 2 * RJ + 1, NC = 2 * E + 1;
+    std::vector<double> K(NR * NC, 0.0);
+    double kmax = 0;
+    for (const Term& t : s.chain) { K[(t.dj + RJ) * NC + t.di + E] = t.coef; kmax = std::max(kmax, std::fabs(t.coef)); }
+    const double tol = 4e-16 * kmax;
+    int best_ops = (int)s.chain.size();
+    bool found = false;
+    for (int r0 = 0; r0 < NR; ++r0) {                       // candidate base row
+        std::vector<double> h(K.begin() + r0 * NC, K.begin() + (r0 + 1) * NC);
+        int hn = 0;
+        for (double v : h) hn += v != 0.0;
+        if (hn < 2) continue;
+        std::vector<double> w(NR, 0.0);
+        std::vector<Term> res;
+        int nterms = 0;
+        for (int r = 0; r < NR; ++r) {
+            const double* kr = &K[r * NC];
+            int rn = 0;
+            for (int c = 0; c < NC; ++c) rn += kr[c] != 0.0;
+            if (rn == 0) continue;
+            double bw = 0; int bres = rn;                   // w = 0: the row stays as plain terms
+            for (int c0 = 0; c0 < NC; ++c0) {
+                if (h[c0] == 0.0 || kr[c0] == 0.0) continue;
+                const double cand = kr[c0] / h[c0];
+                int nres = 0;
+                for (int c = 0; c < NC; ++c) nres += std::fabs(kr[c] - cand * h[c]) > tol;
+                if (nres + 1 < bres + (bw != 0.0)) { bres = nres; bw = cand; }
+            }
+            w[r] = bw;
+            nterms += (bw != 0.0);
+            for (int c = 0; c < NC; ++c) {
+                const double rv = kr[c] - bw * h[c];
+                if (std::fabs(rv) > tol) { res.push_back({0, r - RJ, c - E, rv}); ++nterms; }
+            }
+        }
+        bool unit = false;
+        for (double v : w) unit = unit || v == 1.0;
+        const int ops = hn + (nterms - 1) + (unit ? 0 : 1);
+        if (ops < best_ops) { best_ops = ops; s.fh = h; s.fw = w; s.fres = res; found = true; }
+    }
+    if (!found || best_ops * 5 > (int)s.chain.size() * 4) return false;   // want >= 20 % fewer operations
+    s.factored = true;
+    s.fops = best_ops;
+    return true;
+}
+
+inline std::string lit17(double v) {
+    char b[64];
+    std::snprintf(b, sizeof b, "%.17g", v);
+    std::string t = b;
+    if (t.find_first_of(".eEn") == std::string::npos) t += ".0";
+    return t;
+}
+
+// Scatter form for temporal kernels (drs_sweep2d.cuh): the statements that push one source row
+// into the partial sums of the output rows it touches.  P(dj) is the partial sum of the output
+// row that sees the source row at offset dj (dj = -RJ is that output's first contribution and
+// therefore an assignment, dj = +RJ its last); U(di) is the source row at column offset di.
+// With a row factorisation, DRS_HROW(U) first computes `hacc` = h . u.
+inline void emit_scatter(std::ostringstream& o, const KernelSpec& s) {
+    const int E = s.e, RJ = s.rj;
+    if (s.factored) {
+        o << "#define DRS_FACTORED 1\n#define DRS_HROW(U)";
+        bool first = true;
+        auto hterm = [&](const std::string& operand, double c) {
+            if (first) o << " \\\n    hacc = rmul(" << operand << ", (real)(" << lit17(c) << "));";
+            else o << " \\\n    hacc = rfma(" << operand << ", (real)(" << lit17(c) << "), hacc);";
+            first = false;
+        };
+        if (s.fh[E] != 0.0) hterm("U(0)", s.fh[E]);
+        for (int d = 1; d <= E; ++d) {
+            const double a = s.fh[E - d], b = s.fh[E + d];
+            if (a != 0.0 && a == b) hterm("radd(U(" + std::to_string(-d) + "), U(" + std::to_string(d) + "))", a);
+            else {
+                if (a != 0.0) hterm("U(" + std::to_string(-d) + ")", a);
+                if (b != 0.0) hterm("U(" + std::to_string(d) + ")", b);
+            }
+        }
+        o << "\n";
+    }
+    o << "#define DRS_SCATTER(P, U)";
+    for (int dj = -RJ; dj <= RJ; ++dj) {
+        const std::string P = "P(" + std::to_string(dj) + ")";
+        bool started = dj != -RJ;     // rows after the first accumulate into an existing sum
+        auto add_term = [&](const std::string& operand, double c) {
+            if (!started) {
+                if (c == 1.0) o << " \\\n    " << P << " = " << operand << ";";
+                else o << " \\\n    " << P << " = rmul(" << operand << ", (real)(" << lit17(c) << "));";
+            } else if (c == 1.0) o << " \\\n    " << P << " = radd(" << P << ", " << operand << ");";
+            else o << " \\\n    " << P << " = rfma(" << operand << ", (real)(" << lit17(c) << "), " << P << ");";
+            started = true;
+        };
+        if (s.factored) {
+            if (s.fw[dj + RJ] != 0.0) add_term("hacc", s.fw[dj + RJ]);
+            for (const Term& t : s.fres)
+                if (t.dj == dj) add_term("U(" + std::to_string(t.di) + ")", t.coef);
+        } else {
+            for (const Term& t : s.chain)
+                if (t.dj == dj) add_term("U(" + std::to_string(t.di) + ")", t.coef);
+        }
+        if (!started) o << " \\\n    " << P << " = (real)0;";
+    }
+    o << "\n";
 }
 
 inline void emit_chain(std::ostringstream& o, const char* macro, const std::vector<Term>& terms) {
@@ -193,6 +320,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
     emit_chain(o, "DRS_CHAIN", s.chain);
+    if (s.ts > 1) emit_scatter(o, s);
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
     if (s.tma_ok) o << "#include \"" << (s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
     o << "#include \"drs_gold.cuh\"\n";

@@ -117,6 +117,8 @@ __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {
 // result, so nothing is left to the compiler's contraction rules.
 __device__ __forceinline__ double rmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double rfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ double radd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float radd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float rmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 

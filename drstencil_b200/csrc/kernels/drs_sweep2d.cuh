@@ -8,23 +8,40 @@
 //     reference's `--prefetch` register double-buffer (codegen_2d.hpp:325-337) taken to its
 //     hardware form; out-of-grid rows/columns are zero-filled by the TMA unit, so there is
 //     no bounds logic on the load side;
-//   * the row window the reference keeps in shared memory (`in_shm[Range][...]`,
-//     codegen_2d.hpp:166-172) lives in registers, rotated statically (the row loop is
-//     unrolled by the window height), each thread owning DRS_VT 128-bit vectors of adjacent
-//     columns (the reference's --block-merge-x);
-//   * `--step n` in temporal mode runs n sub-steps per sweep: level s of the register
-//     window holds rows of time level s; x neighbours of levels >= 1 come from the adjacent
-//     lanes by warp shuffle, so a warp loses E columns per level at each edge and strips
-//     overlap by 2*HW columns; the levels of one iteration are evaluated top-down so that
-//     their chains are independent of each other;
-//   * every output is produced by one explicitly ordered mul/fma chain (DRS_CHAIN, gold
-//     order: drstencil_2d.hpp:164-178) and stored once (no STG + atomicAdd double touch,
-//     codegen_2d.hpp:345-366), with a 128-bit store where the vector is fully interior.
+//   * each thread owns DRS_VT 128-bit vectors of adjacent columns (the reference's
+//     --block-merge-x); every output is stored once, 128 bits at a time where the vector is
+//     fully interior (no STG + atomicAdd double touch, codegen_2d.hpp:345-366).
 //
-// Generated translation unit must define: DRS_T DRS_NAME DRS_RJ DRS_E DRS_TS
-// DRS_CHAIN(MUL,FMA) DRS_NW DRS_ST DRS_RB DRS_VT DRS_MINB.
+// Two evaluation schemes, chosen by the temporal depth DRS_TS:
+//
+//   DRS_TS == 1  GATHER, bit-exact.  The row window the reference keeps in shared memory
+//     (`in_shm[Range][...]`, codegen_2d.hpp:166-172) lives in registers, rotated statically (the
+//     row loop is unrolled by the window height); each output is one explicitly ordered mul/fma
+//     chain over that window (DRS_CHAIN, gold order: drstencil_2d.hpp:164-178), so results equal
+//     the reference's gold kernel bit for bit.
+//
+//   DRS_TS > 1   SCATTER, temporal blocking (`--step n` as n in-kernel sub-steps, results within
+//     1e-12 of the composed operator).  A row of time level s-1 is pushed into the partial sums
+//     of the 2*RJ+1 level-s rows it touches -- the reference's forward/backward accumulation idea
+//     (drstencil_2d.hpp:180-228) done in registers instead of through global atomics.  State per
+//     level is just those partial sums (`pw[s][2*RJ+1][C]`); the slot completed in one iteration is
+//     consumed by level s+1 in the next one and then re-initialised, levels are evaluated top-down
+//     so the TS chains of an iteration are independent, and x neighbours of levels >= 1 come from
+//     the adjacent lanes by warp shuffle (a warp loses E columns per level at each edge: strips
+//     overlap by 2*HW columns).  With DRS_FACTORED the generator has found rows of the operator
+//     that are multiples of one row vector h (generate.hpp: factorise_rows): H = h . u is computed
+//     once per row (DRS_HROW) and scattered with the row weights (2d9pt_box: 6 operations per
+//     update instead of 9).
+//
+// Generated translation unit must define: DRS_T DRS_NAME DRS_RJ DRS_E DRS_TS DRS_NW DRS_ST DRS_RB
+// DRS_VT DRS_MINB, DRS_CHAIN(MUL,FMA) and, for DRS_TS > 1, DRS_SCATTER(P,U) [+ DRS_FACTORED,
+// DRS_HROW(U)].
 #pragma once
 #include "drs_common.cuh"
+
+#ifndef DRS_FACTORED
+#define DRS_FACTORED 0
+#endif
 
 namespace drs {
 namespace s2d {
@@ -32,10 +49,10 @@ namespace s2d {
 constexpr int RJ = DRS_RJ;          // max |dj| of the sub-step operator
 constexpr int E = DRS_E;            // max |di|
 constexpr int TS = DRS_TS;          // sub-steps (time levels) per sweep
-constexpr int R2 = 2 * RJ + 1;      // register window height
-constexpr int VT = DRS_VT;          // 128-bit vectors per thread (the reference's --block-merge-x)
+constexpr int R2 = 2 * RJ + 1;      // rows an output depends on / rows an input contributes to
+constexpr int VT = DRS_VT;          // 128-bit vectors per thread
 constexpr int C = VT * kVec;        // consecutive columns a thread owns
-constexpr int VW = C + 2 * E;       // register window width per thread
+constexpr int VW = C + 2 * E;       // a row as one thread sees it: own columns + E neighbours per side
 constexpr int E0 = ((E + kVec - 1) / kVec) * kVec;               // smem halo columns per side
 constexpr int HW = (((TS - 1) * E + kVec - 1) / kVec) * kVec;    // strip overlap per side
 constexpr int WT = 32 * C;          // columns a warp computes per row
@@ -45,88 +62,121 @@ constexpr int ST = DRS_ST, RB = DRS_RB, NW = DRS_NW;
 constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);
 constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
+// iterations between a row entering and the output that completes with it leaving
+constexpr int DEPTH = TS == 1 ? R2 : 2 * TS * RJ + TS - 1;
+// register state: gather keeps R2 input rows, scatter keeps R2 partial-sum rows per level
+constexpr int NLV = TS;
+constexpr int SW = TS == 1 ? VW : C;
 static_assert((ST & (ST - 1)) == 0 && (RB & (RB - 1)) == 0, "stages and rows/stage are powers of two");
 static_assert(TS == 1 || E <= C, "shuffle exchange reaches one lane");
 static_assert(WB <= 256, "TMA box is at most 256 elements wide");
 static_assert(WU > 0, "strip overlap leaves no useful columns");
 
-// physical slot of the window row at offset dj when the newest row sits in slot PH
-template <int PH>
-__device__ __forceinline__ constexpr int slot(int dj) { return (PH + dj - RJ + 2 * R2) % R2; }
+__device__ __forceinline__ constexpr int mod_r2(int v) { return ((v % R2) + R2) % R2; }
 
 struct Tile {
     int lane;
     int x_first;       // global column of this thread's element 0
-    int v_lo, v_hi;    // storable elements of the vector: v_lo <= v < v_hi
-    drs_i64 y_out0;    // output row produced at iteration 0 (may lie before the chunk)
+    int v_lo, v_hi;    // storable elements of the thread's columns: v_lo <= v < v_hi
+    drs_i64 y_out0;    // output row produced at iteration 0 (lies before the chunk)
     int n_first;       // first iteration whose output row is inside the chunk
     int n_end;         // one past the last such iteration
     drs_i64 N;
     real* out;
 };
 
-// One iteration of the row pipeline.  Levels are evaluated TOP-DOWN: level s reads the window of
-// level s-1 as the previous iteration left it, so the TS chains of one iteration are mutually
-// independent (instruction-level parallelism across time levels) and the shared-memory loads of
-// the new input row are off the critical path.  The price is one iteration of delay per level:
-// the row produced for level s at iteration n is  yrow0 + n - s*(RJ + 1).
-template <int PH>
-__device__ __forceinline__ void row_step(real (&w)[TS][R2][VW], const real* __restrict__ srow, const Tile& t,
-                                         int n) {
-    constexpr int PP = (PH + R2 - 1) % R2;   // phase the windows were left in by the previous iteration
+__device__ __forceinline__ void store_row(const Tile& t, int n, const real (&o)[C]) {
+    real* dst = t.out + (t.y_out0 + n) * t.N + t.x_first;
+    if (t.v_lo <= 0 && t.v_hi >= C) {
 #pragma unroll
-    for (int s = TS; s >= 1; --s) {
+        for (int j = 0; j < VT; ++j) {
+            real ov[kVec];
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) ov[v] = o[j * kVec + v];
+            stg_vec(dst + j * kVec, ov);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < C; ++v)
+            if (v >= t.v_lo && v < t.v_hi) dst[v] = o[v];
+    }
+}
+
+// this thread's view of a staged input row: own columns + E neighbours per side
+__device__ __forceinline__ void load_row(real (&u)[VW], const real* __restrict__ srow, int lane) {
+    const real* own = srow + E0 + lane * C;
+#pragma unroll
+    for (int j = 0; j < VT; ++j) {
+        real tmp[kVec];
+        lds_vec(tmp, own + j * kVec);
+#pragma unroll
+        for (int v = 0; v < kVec; ++v) u[E + j * kVec + v] = tmp[v];
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        u[e] = own[e - E];
+        u[E + C + e] = own[C + e];
+    }
+}
+
+// One iteration of the row pipeline; PH = iteration mod R2 (compile-time: static rotation).
+template <int PH>
+__device__ __forceinline__ void row_step(real (&w)[NLV][R2][SW], const real* __restrict__ srow, const Tile& t, int n) {
+    if constexpr (TS == 1) {
+        // ---- gather: output row from the window as the previous iteration left it, then the new
+        //      row replaces the oldest one (its loads are off the chain's critical path) ----
+        constexpr int PP = mod_r2(PH - 1);     // slot of the newest row before this iteration's insert
         real o[C];
 #pragma unroll
         for (int v = 0; v < C; ++v) {
             real acc;
-#define DRS_MUL_(dk, dj, di, c) acc = rmul(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c));
-#define DRS_FMA_(dk, dj, di, c) acc = rfma(w[s - 1][slot<PP>(dj)][E + v + (di)], (real)(c), acc);
+#define DRS_W_(dj) w[0][mod_r2(PP + (dj) - RJ)]
+#define DRS_MUL_(dk, dj, di, c) acc = rmul(DRS_W_(dj)[E + v + (di)], (real)(c));
+#define DRS_FMA_(dk, dj, di, c) acc = rfma(DRS_W_(dj)[E + v + (di)], (real)(c), acc);
             DRS_CHAIN(DRS_MUL_, DRS_FMA_)
 #undef DRS_MUL_
 #undef DRS_FMA_
+#undef DRS_W_
             o[v] = acc;
         }
-        if (s < TS) {
-            // becomes the newest row of level s; x neighbours from the adjacent lanes
+        if (n >= t.n_first && n < t.n_end) store_row(t, n, o);
+        load_row(w[0][PH], srow, t.lane);
+    } else {
+        // ---- scatter, levels top-down ----
 #pragma unroll
-            for (int v = 0; v < C; ++v) w[s < TS ? s : 0][PH][E + v] = o[v];
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                w[s < TS ? s : 0][PH][e] = __shfl_up_sync(0xffffffffu, o[C - E + e], 1);
-                w[s < TS ? s : 0][PH][E + C + e] = __shfl_down_sync(0xffffffffu, o[e], 1);
-            }
-        } else if (n >= t.n_first && n < t.n_end) {
-            real* dst = t.out + (t.y_out0 + n) * t.N + t.x_first;
-            if (t.v_lo <= 0 && t.v_hi >= C) {
-#pragma unroll
-                for (int j = 0; j < VT; ++j) {
-                    real ov[kVec];
-#pragma unroll
-                    for (int v = 0; v < kVec; ++v) ov[v] = o[j * kVec + v];
-                    stg_vec(dst + j * kVec, ov);
-                }
+        for (int s = TS; s >= 1; --s) {
+            real u[VW];
+            if (s == 1) {
+                load_row(u, srow, t.lane);
             } else {
+                // the level s-1 row completed by the previous iteration; neighbours by shuffle
+                const real (&src)[SW] = w[s >= 2 ? s - 2 : 0][mod_r2(PH - 1 - RJ)];
 #pragma unroll
-                for (int v = 0; v < C; ++v)
-                    if (v >= t.v_lo && v < t.v_hi) dst[v] = o[v];
+                for (int v = 0; v < C; ++v) u[E + v] = src[v];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    u[e] = __shfl_up_sync(0xffffffffu, src[C - E + e], 1);
+                    u[E + C + e] = __shfl_down_sync(0xffffffffu, src[e], 1);
+                }
             }
-        }
-    }
-    // ---- level 0: this thread's vector plus E halo columns each side, from the staged row ----
-    {
-        const real* own = srow + E0 + t.lane * C;
 #pragma unroll
-        for (int j = 0; j < VT; ++j) {
-            real tmp[kVec];
-            lds_vec(tmp, own + j * kVec);
+            for (int v = 0; v < C; ++v) {
+#define DRS_U_(di) u[E + v + (di)]
+#define DRS_P_(dj) w[s - 1][mod_r2(PH - (dj))][v]
+#if DRS_FACTORED
+                real hacc;
+                DRS_HROW(DRS_U_)
+#endif
+                DRS_SCATTER(DRS_P_, DRS_U_)
+#undef DRS_U_
+#undef DRS_P_
+            }
+            if (s == TS && n >= t.n_first && n < t.n_end) {
+                real o[C];
 #pragma unroll
-            for (int v = 0; v < kVec; ++v) w[0][PH][E + j * kVec + v] = tmp[v];
-        }
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            w[0][PH][e] = own[e - E];
-            w[0][PH][E + C + e] = own[C + e];
+                for (int v = 0; v < C; ++v) o[v] = w[TS - 1][mod_r2(PH - RJ)][v];
+                store_row(t, n, o);
+            }
         }
     }
 }
@@ -150,7 +200,7 @@ struct Stream {
 // One input row: wait for its stage if it is the stage's first row, run the row through every
 // time level, hand the stage back to the TMA unit if it was the stage's last row.
 template <int PH>
-__device__ __forceinline__ bool iteration(real (&w)[TS][R2][VW], const Stream& st, const Tile& t, int n) {
+__device__ __forceinline__ bool iteration(real (&w)[NLV][R2][SW], const Stream& st, const Tile& t, int n) {
     const int rr = n & (RB - 1);
     const int c = n / RB;
     const int s = c & (ST - 1);
@@ -169,9 +219,9 @@ __device__ __forceinline__ bool iteration(real (&w)[TS][R2][VW], const Stream& s
     return true;
 }
 
-// R2 consecutive rows with the window phase known at compile time (static register rotation)
+// R2 consecutive rows with the phase known at compile time (static register rotation)
 template <int PH>
-__device__ __forceinline__ bool phases(real (&w)[TS][R2][VW], const Stream& st, const Tile& t, int n0) {
+__device__ __forceinline__ bool phases(real (&w)[NLV][R2][SW], const Stream& st, const Tile& t, int n0) {
     if constexpr (PH < R2) {
         if (!iteration<PH>(w, st, t, n0 + PH)) return false;
         return phases<PH + 1>(w, st, t, n0);
@@ -206,13 +256,13 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const int X0 = (H / kVec) * kVec + xs * WU - HW;   // column of lane 0, element 0
     const drs_i64 ya = p.slow_lo + (drs_i64)yc * p.chunk;
     const drs_i64 yb = (ya + p.chunk < p.slow_hi) ? ya + p.chunk : p.slow_hi;
-    // iterations: chunk rows + pipeline depth (one window height per level), rounded up to whole
-    // window rotations so that the unrolled phases need no guard; the surplus iterations stream
-    // rows past the chunk (or zero fill) and store nothing
-    const int n_end = (int)(yb - ya) + TS * R2;
+    // iterations: chunk rows + pipeline depth, rounded up to whole rotations so that the unrolled
+    // phases need no guard; the surplus iterations stream rows past the chunk (or zero fill) and
+    // store nothing
+    const int n_end = (int)(yb - ya) + DEPTH;
     st.NIT = (n_end + R2 - 1) / R2 * R2;
     st.NCH = (st.NIT + RB - 1) / RB;
-    st.yrow0 = (int)(ya - TS * RJ);
+    st.yrow0 = (int)(ya - TS * RJ);                     // first input row the chunk depends on
     st.x_box = X0 - E0;
 
     Tile t;
@@ -224,9 +274,9 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         t.v_lo = (int)(lo - t.x_first);
         t.v_hi = (int)(hi - t.x_first);
     }
-    t.n_first = TS * R2;
+    t.n_first = DEPTH;
     t.n_end = n_end;
-    t.y_out0 = ya - TS * R2;
+    t.y_out0 = ya - DEPTH;
     t.N = p.N;
     t.out = p.out;
 
@@ -234,13 +284,13 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         for (int c = 0; c < ST && c < st.NCH; ++c) st.issue(c);
     }
 
-    real w[TS][R2][VW];
+    real w[NLV][R2][SW];
 #pragma unroll
-    for (int s = 0; s < TS; ++s)
+    for (int s = 0; s < NLV; ++s)
 #pragma unroll
         for (int r = 0; r < R2; ++r)
 #pragma unroll
-            for (int x = 0; x < VW; ++x) w[s][r][x] = (real)0;
+            for (int x = 0; x < SW; ++x) w[s][r][x] = (real)0;
 
 #pragma unroll 1
     for (int n0 = 0; n0 < st.NIT; n0 += R2) {

@@ -136,7 +136,10 @@ def filter_config(c: Config, dim: int, radius: int, esize: int = 8) -> bool:
             return False
         stage = (c.s_unroll * wb * esize + 127) // 128 * 128
         smem = warps * c.stages * (stage + 8)
-        live = (c.step if c.fuse == "temporal" else 1) * (2 * radius + 1) * (cols + 2 * e) * (esize // 4)
+        if c.fuse == "temporal" and c.step > 1:      # scatter: partial sums per level + the row in flight
+            live = (c.step * (2 * radius + 1) * cols + 2 * (cols + 2 * e)) * (esize // 4)
+        else:
+            live = (2 * radius + 1) * (cols + 2 * e) * (esize // 4)
     else:
         ry = c.rows_3d or 8
         wb = 32 * vec + 2 * ((radius + vec - 1) // vec * vec)
