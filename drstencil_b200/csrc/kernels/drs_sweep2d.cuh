@@ -122,7 +122,8 @@ __device__ __forceinline__ void load_row(real (&u)[VW], const real* __restrict__
 // One iteration of the row pipeline; PH = iteration mod R2 (compile-time: static rotation).
 template <int PH>
 __device__ __forceinline__ void row_step(real (&w)[NLV][R2][SW], const real* __restrict__ srow, const Tile& t, int n) {
-    if constexpr (TS == 1) {
+#if DRS_TS == 1
+    {
         // ---- gather: output row from the window as the previous iteration left it, then the new
         //      row replaces the oldest one (its loads are off the chain's critical path) ----
         constexpr int PP = mod_r2(PH - 1);     // slot of the newest row before this iteration's insert
@@ -141,7 +142,9 @@ __device__ __forceinline__ void row_step(real (&w)[NLV][R2][SW], const real* __r
         }
         if (n >= t.n_first && n < t.n_end) store_row(t, n, o);
         load_row(w[0][PH], srow, t.lane);
-    } else {
+    }
+#else
+    {
         // ---- scatter, levels top-down ----
 #pragma unroll
         for (int s = TS; s >= 1; --s) {
@@ -179,6 +182,7 @@ __device__ __forceinline__ void row_step(real (&w)[NLV][R2][SW], const real* __r
             }
         }
     }
+#endif
 }
 
 // Per-warp streaming state that does not change across iterations.
