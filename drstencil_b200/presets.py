@@ -29,5 +29,5 @@ PRESETS = {
     "c2": (_p("baseline", "c2_2d9pt_box.stc"), Knobs(step=4, sn=256, vectors=2, stages=2)),
     "c3": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32", sn=64)),
     "c4": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(sn=16, rows_3d=4)),
-    "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(sn=16, rows_3d=4)),
+    "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(sn=16, rows_3d=6)),
 }

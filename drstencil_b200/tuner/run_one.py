@@ -35,9 +35,12 @@ def main():
     ap.add_argument("--3d", dest="is3d", action="store_true")
     ap.add_argument("--size", type=int, nargs="+")
     ap.add_argument("--launches", type=int, default=6)
-    ap.add_argument("rest", nargs=argparse.REMAINDER)
-    a = ap.parse_args()
-    rest = [x for x in a.rest if x != "--"]
+    argv = sys.argv[1:]
+    rest = []
+    if "--" in argv:
+        cut = argv.index("--")
+        argv, rest = argv[:cut], argv[cut + 1:]
+    a = ap.parse_args(argv)
     kn = knobs_from_argv(rest)
     st = Stencil.from_file(a.stc, a.is3d or None)
     if a.size:

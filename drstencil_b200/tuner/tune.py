@@ -100,10 +100,8 @@ def profile(stc, st, cfg: Config):
     """Nsight Compute, named metrics, on tuner/run_one.py for this configuration."""
     size = [str(n) for n in st.shape]
     cmd = ["ncu", "--metrics", ",".join(ncu_metrics.METRICS), "--clock-control", "none", "-k", "regex:dr_", "-s", "2",
-           "-c", "3", "--csv", sys.executable, "-m", "drstencil_b200.tuner.run_one", stc, "--size"] + size + \
-          ["--launches", "6", "--"] + cfg_to_command_line(cfg).split()
-    if st.dim == 3:
-        cmd.insert(cmd.index(stc) + 1, "--3d")
+           "-c", "3", "--csv", sys.executable, "-m", "drstencil_b200.tuner.run_one", stc] + \
+          (["--3d"] if st.dim == 3 else []) + ["--size"] + size + ["--launches", "6", "--"] + cfg_to_command_line(cfg).split()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     rows = ncu_metrics.parse(r.stdout)
     s = ncu_metrics.summarise(rows)

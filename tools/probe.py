@@ -54,16 +54,12 @@ def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     out = []
     variants = {
-        "c1": [dict(sn=256, warps=1, min_blocks=16), dict(step=2, sn=256), dict(step=2, sn=256, vectors=2), dict(step=5, sn=512, vectors=2)],
-        "c2": [dict(step=4, sn=256, vectors=2), dict(step=4, sn=256, vectors=2, min_blocks=4), dict(step=4, sn=256, vectors=2, min_blocks=6),
-               dict(step=4, sn=256, vectors=2, min_blocks=7), dict(step=4, sn=512, vectors=2, min_blocks=6),
-               dict(step=4, sn=256, vectors=2, no_factor=1), dict(step=4, sn=256, vectors=1), dict(step=4, sn=256, vectors=1, min_blocks=10),
-               dict(step=4, sn=256, vectors=2, warps=1), dict(step=4, sn=256, vectors=2, warps=4), dict(step=4, sn=256, vectors=2, stages=2),
-               dict(step=4, sn=256, vectors=2, rows_per_stage=8), dict(step=4, sn=256, vectors=2, rows_per_stage=2),
-               dict(step=2, sn=256, vectors=2), dict(step=3, sn=256, vectors=2), dict(step=6, sn=512, vectors=2), dict(step=8, sn=512, vectors=2)],
-        "c3": [dict(dtype="f32", sn=64), dict(dtype="f32", step=2, sn=256), dict(dtype="f32", step=3, sn=256), dict(dtype="f32", step=4, sn=256)],
-        "c4": [dict(sn=16, rows_3d=4)],
-        "c5": [dict(sn=16, rows_3d=4)],
+        "c1": [dict(sn=256, warps=1, min_blocks=16)],
+        "c2": [dict(step=4, sn=256, vectors=2, stages=2)],
+        "c3": [dict(dtype="f32", sn=64)],
+        "c4": [dict(sn=16, rows_3d=4), dict(sn=16, rows_3d=8), dict(sn=16, rows_3d=6), dict(sn=16, rows_3d=12, warps=1)],
+        "c5": [dict(sn=16, rows_3d=4), dict(sn=16, rows_3d=8), dict(sn=8, rows_3d=8), dict(sn=32, rows_3d=8), dict(sn=16, rows_3d=8, warps=4),
+               dict(sn=16, rows_3d=8, warps=1), dict(sn=16, rows_3d=6), dict(sn=16, rows_3d=8, stages=8)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
