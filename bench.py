@@ -209,7 +209,6 @@ def run_single(args, rank, world):
     path, kn = PRESETS[preset]
     st = drs.Stencil.from_file(path)
     plan = drs.Plan(st, kn)
-    info = plan.info
     shape = st.shape
     dtype = torch.float32 if kn.dtype == drs.F32 else torch.float64
     esize = 4 if kn.dtype == drs.F32 else 8
@@ -226,6 +225,7 @@ def run_single(args, rank, world):
     sampler.start()
     secs, launches = time_steps(plan, A, B, timesteps, args.steps, args.warmup)
     clocks = sampler.stop()
+    info = plan.info
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([secs], device="cuda", dtype=torch.float64)
@@ -319,12 +319,25 @@ def per_config(args):
             info = plan.info
             upd = interior_points(shape, info.halo) * drs.sweep_count(ts, kn.step) * kn.step * k
             ach = all_points(shape) * 2 * esize / (secs / launches) / 1e9
+            # what a plain device copy of the same array reaches (small grids cannot reach the big-copy peak)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                B.copy_(A)
+            e0.record()
+            for _ in range(10):
+                B.copy_(A)
+            e1.record()
+            torch.cuda.synchronize()
+            copy_gbs = all_points(shape) * 2 * esize / (e0.elapsed_time(e1) * 1e-4) / 1e9
             out.append({"workload": "%s: %s" % (wl, desc), "value": upd / secs / 1e9, "unit": "GStencil/s",
                         "temporal_depth": kn.step, "kernel": info.kernel_name, "launch_ms": secs / launches * 1e3,
                         "gpu_launches": launches, "n_gpus": 1,
                         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                      "gstencil_roofline": peak / (2 * esize) * kn.step,
-                                     "frac_of_single_step_gstencil_roofline": (upd / secs / 1e9) / (peak / (2 * esize))}})
+                                     "frac_of_single_step_gstencil_roofline": (upd / secs / 1e9) / (peak / (2 * esize)),
+                                     "torch_copy_same_array_gbs": copy_gbs,
+                                     "traffic": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(info.kernel_name)
+                                                 if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")) else None)}})
             del A, B, plan
             torch.cuda.empty_cache()
         except Exception as e:
