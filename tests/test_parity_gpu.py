@@ -221,3 +221,48 @@ def test_linearity_and_idempotence_at_scale(built):
     og = torch.zeros_like(x)
     plan.gold_sweep(x, og)
     assert torch.equal(og, ox)
+
+
+@pytest.mark.parametrize("name,shape,kn", [
+    ("2d5pt_star", (70, 136), dict(sn=16)), ("2d9pt_box", (90, 264), dict(step=4, vectors=2, sn=24)),
+    ("2d25pt_box", (61, 200), dict(step=2)), ("3d7pt_star", (14, 21, 70), dict(sn=5, rows_3d=4)),
+    ("3d9pt_cross", (12, 18, 66), dict()),
+])
+def test_no_write_outside_the_interior(built, name, shape, kn):
+    """Guard bands (compute-sanitizer is closed on this pool): the destination sits inside a larger
+    poisoned allocation; a sweep may change nothing but the interior -- neither the guard bands
+    before/after the array nor the frozen Halo ring."""
+    import torch
+    plan = _plan(name, shape, **kn)
+    n = int(np.prod(shape))
+    pad = 4096
+    src = torch.rand(n + 2 * pad, dtype=torch.float64, device="cuda")
+    dst = torch.full((n + 2 * pad,), -777.0, dtype=torch.float64, device="cuda")
+    a = src[pad:pad + n].view(shape)
+    b = dst[pad:pad + n].view(shape)
+    assert a.data_ptr() % 16 == 0 and b.is_contiguous()
+    plan.sweep(a, b)
+    plan.sync_check()
+    H = plan.halo
+    assert torch.all(dst[:pad] == -777.0) and torch.all(dst[pad + n:] == -777.0)
+    ring = torch.ones(shape, dtype=torch.bool, device="cuda")
+    ring[tuple(slice(H, -H) for _ in shape)] = False
+    assert torch.all(b[ring] == -777.0)
+    assert not torch.any(b[~ring] == -777.0)
+
+
+def test_degenerate_grids(built):
+    """Grids with an empty interior, or thinner than one tile, are legal and write nothing / little."""
+    import torch
+    for name, shape in [("2d9pt_star", (4, 64)), ("2d5pt_star", (3, 8)), ("3d7pt_star", (2, 8, 8)), ("2d25pt_box", (5, 6))]:
+        plan = _plan(name, shape)
+        a = torch.rand(shape, dtype=torch.float64, device="cuda")
+        b = torch.full(shape, -5.0, dtype=torch.float64, device="cuda")
+        plan.sweep(a, b)
+        plan.sync_check()
+        from oracle import oracle
+        offs, coefs, halo = oracle_terms(name, 1)
+        ref = np.full(shape, -5.0)
+        if all(n > 2 * halo for n in shape):
+            oracle.sweep(a.cpu().numpy(), ref, offs, coefs, halo)
+        assert np.array_equal(b.cpu().numpy(), ref), (name, shape)
