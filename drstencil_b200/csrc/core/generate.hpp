@@ -118,12 +118,16 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     // --- geometry ---
     const long long slow = s.dim == 3 ? st.L : st.M;
     const long long slow_out = std::max<long long>(1, slow - 2 * s.halo);
+    // defaults distilled from the tuner runs on B200 (profiles/r01_tune_*.json): two warps per CTA,
+    // a shallow ring (the many resident warps provide the bytes in flight), fp64 threads own two
+    // 128-bit vectors, chunks sized so that a large grid yields several thousand tiles
     if (s.dim == 2) {
-        s.nw = 2; s.st = 4; s.rb = 4;
-        s.chunk = 128;
-        s.vt = 1;
+        s.nw = 2; s.st = 2;
+        s.rb = s.dtype == DRS_F64 ? 4 : 8;
+        s.vt = s.dtype == DRS_F64 ? 2 : 1;
+        s.chunk = s.dtype == DRS_F64 ? (st.M >= 8192 ? 256 : 128) : (st.M >= 8192 ? 32 : 64);
     } else {
-        s.nw = 2; s.ry = 8; s.chunk = 64;
+        s.nw = 2; s.ry = s.rk <= 1 ? 4 : 8; s.chunk = 16;
         s.st = pow2_ceil(2 * s.rk + 2);
         if (s.st < 4) s.st = 4;
     }

@@ -54,6 +54,13 @@ CASES = {
                    ["--streaming", "--bx", "128", "--sn", "64", "--cyclic-merge-x", "2", "--prefetch"]),
     "full_c4": ("3d7pt_star", True, (768, 768, 768), 4, 1, ["--bx", "32", "--by", "8", "--sn", "32"]),
 }
+# the eight shipped descriptions at the reference's own sizes (8192^2 / 512^3) and its tuner's fixed
+# --step 2 (benchmarks/*/tuning.py: `range(2, 3)`), typical streaming options: head-to-head table
+_S2D = ["--streaming", "--bx", "128", "--sn", "64", "--cyclic-merge-x", "2", "--prefetch"]
+for _n in ("2d5pt_star", "2d5pt_cross", "2d9pt_star", "2d9pt_box", "2d9pt_cross", "2d25pt_box"):
+    CASES["ship_" + _n] = (_n, False, (1, 8192, 8192), 4, 2, _S2D)
+for _n in ("3d7pt_star", "3d9pt_cross"):
+    CASES["ship_" + _n] = (_n, True, (512, 512, 512), 4, 2, ["--bx", "32", "--by", "8", "--sn", "32"])
 
 
 def sh(cmd, **kw):

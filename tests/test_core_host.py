@@ -125,7 +125,7 @@ def test_plan_specialisation_text(built):
     assert src.index("MUL(0, 0, -1") < src.index("FMA(0, -1, 0") < src.index("FMA(0, 0, 0, 0.3)")
     assert "drs_sweep2d.cuh" in src
     info = plan.info
-    assert info.halo == 1 and info.kernel_name == "dr_2d5pt_star"
+    assert info.halo == 1 and info.kernel_name == "dr_2d5pt_star" and info.tile_x == 128
     # temporal depth 4: base chain in the sweep, composed 81-term chain in the gold kernel
     st = drs.Stencil.from_file(stc_path("2d9pt_box")).set_size((256, 256))
     plan = drs.Plan(st, drs.Knobs(step=4))

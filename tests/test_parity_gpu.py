@@ -266,3 +266,77 @@ def test_degenerate_grids(built):
         if all(n > 2 * halo for n in shape):
             oracle.sweep(a.cpu().numpy(), ref, offs, coefs, halo)
         assert np.array_equal(b.cpu().numpy(), ref), (name, shape)
+
+
+@pytest.mark.parametrize("preset,bar", [("c1", 0.0), ("c2", 1e-12), ("c3", 0.0), ("c4", 0.0)])
+def test_baseline_sizes_against_the_gold_kernel(built, preset, bar):
+    """BASELINE.json sizes (4096^2, 16384^2 depth 4, 16384^2 fp32, 768^3): one sweep of the tuned
+    plan against the device gold kernel (itself bit-exact against the oracle at small sizes) --
+    bit-identical for depth 1, <= 1e-12 relative for the temporally fused config."""
+    import torch
+    import drstencil_b200 as drs
+    from drstencil_b200.presets import PRESETS
+    path, kn = PRESETS[preset]
+    st = drs.Stencil.from_file(path)
+    plan = drs.Plan(st, kn)
+    dt = torch.float32 if kn.dtype == drs.F32 else torch.float64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.rand(st.shape, dtype=dt, device="cuda", generator=g)
+    b = torch.zeros_like(a)
+    ref = torch.zeros_like(a)
+    plan.sweep(a, b)
+    plan.gold_sweep(a, ref)
+    plan.sync_check()
+    if bar == 0.0:
+        assert torch.equal(b, ref)
+    else:
+        mx, rms = plan.check_error(b, ref)
+        assert mx / float(ref.abs().max()) <= bar
+    # checksum of checksums: row sums of the result, summed, equal in both
+    assert abs(float(b.double().sum()) - float(ref.double().sum())) <= 1e-9 * abs(float(ref.double().sum()))
+
+
+def test_streams_many_plans_and_argument_errors(built):
+    import torch
+    import drstencil_b200 as drs
+    from oracle import oracle
+    shape = (96, 128)
+    a0 = oracle.rand_array(shape)
+    refA, refB = oracle_run("2d9pt_box", 1, shape, 1)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for k in range(6):                                # several live plans, alternating streams
+        plan = _plan("2d9pt_box", shape, sn=8 + 4 * k)
+        A, B = _dev(a0), _dev(np.zeros(shape))
+        torch.cuda.synchronize()
+        st = s1 if k % 2 == 0 else s2
+        with torch.cuda.stream(st):
+            plan.sweep(A, B)                          # picks up torch's current stream
+        plan.sync_check(st)
+        outs.append(B.cpu().numpy())
+        del plan
+    assert all(np.array_equal(o, refB) for o in outs)
+    plan = _plan("2d9pt_box", shape)
+    A = _dev(a0)
+    with pytest.raises(drs.DrsError) as e:
+        plan.sweep(A, A)                              # in-place is not allowed (the reference requires in != out too)
+    assert e.value.code == drs.E_ARG
+    flat = torch.zeros(shape[0] * shape[1] + 1, dtype=torch.float64, device="cuda")
+    with pytest.raises(drs.DrsError) as e:
+        plan.sweep(flat[1:].view(shape), _dev(np.zeros(shape)))   # 8-byte aligned only: no TMA descriptor
+    assert e.value.code == drs.E_ARG
+
+
+@pytest.mark.parametrize("name", ["2d5pt_cross", "2d9pt_cross", "2d9pt_star", "2d25pt_box"])
+def test_fp32_temporal_all_shapes(built, name):
+    from oracle import oracle
+    shape = (160, 264)
+    plan = _plan(name, shape, dtype="f32", step=2)
+    a64 = oracle.rand_array(shape)
+    A, B = _dev(a64.astype(np.float32)), _dev(np.zeros(shape, np.float32))
+    plan.run(A, B, iterations=4)
+    plan.sync_check()
+    ref64, _ = oracle_run(name, 2, shape, 2, np.float64, a0=a64)
+    H = plan.halo
+    inner = (slice(H, -H), slice(H, -H))
+    assert max_rel(A.cpu().numpy()[inner], ref64[inner]) <= 1e-5
