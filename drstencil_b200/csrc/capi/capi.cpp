@@ -250,6 +250,7 @@ struct drs_plan {
     double* d_res = nullptr;
     std::map<const void*, CUtensorMap> tmaps;
     void* h_dev[2] = {nullptr, nullptr};  // buffers owned by drs_run_host
+    void* scratch[2] = {nullptr, nullptr};  // intermediate time levels of multi-launch 3D temporal sweeps
     long long launches = 0;
     // slab mode
     bool slab = false;
@@ -334,14 +335,15 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     return DRS_OK;
 }
 
-void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q) {
+// ring = frozen ring width of this launch (spec.halo, or the sub-step's share of it)
+void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int ring = -1) {
     const drs::KernelSpec& s = p->spec;
     std::memset(&q, 0, sizeof q);
     q.in = in; q.out = out;
     q.L = p->st.L; q.M = p->st.M; q.N = p->st.N;
-    q.halo = s.halo;
+    q.halo = ring >= 0 ? ring : s.halo;
     const long long slow = p->local_slow();
-    if (!p->slab) { q.slow_lo = s.halo; q.slow_hi = slow - s.halo; }
+    if (!p->slab) { q.slow_lo = q.halo; q.slow_hi = slow - q.halo; }
     else {
         const long long ghost = s.halo, org = p->lo - ghost;  // global index of local plane 0
         const long long glo = std::max<long long>(p->lo, s.halo), ghi = std::min<long long>(p->hi, p->g_slow - s.halo);
@@ -360,13 +362,13 @@ void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q) {
         }
     }
     if (q.slow_hi < q.slow_lo) q.slow_hi = q.slow_lo;
-    const long long a0 = (s.halo / s.vec()) * s.vec();
-    const long long xspan = std::max<long long>(0, (q.N - s.halo) - a0);
+    const long long a0 = (q.halo / s.vec()) * s.vec();
+    const long long xspan = std::max<long long>(0, (q.N - q.halo) - a0);
     q.nxs = (int)((xspan + s.wu() - 1) / s.wu());
     const long long nslow = (q.slow_hi - q.slow_lo + s.chunk - 1) / s.chunk;
     if (s.dim == 2) { q.nys = (int)nslow; q.nzs = 1; }
     else {
-        const long long yspan = std::max<long long>(0, q.M - 2 * s.halo);
+        const long long yspan = std::max<long long>(0, q.M - 2 * q.halo);
         q.nys = (int)((yspan + s.ry - 1) / s.ry);
         q.nzs = (int)nslow;
     }
@@ -386,14 +388,35 @@ int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     return DRS_OK;
 }
 
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring);
+
 int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     if (in == out) return fail(DRS_E_ARG, "d_in and d_out must differ");
     if (!p->spec.tma_ok) return launch_gold(p, in, out, stream);
+    const int T = p->spec.sub_launches;
+    if (T <= 1) return launch_one(p, in, out, stream, -1);
+    // sub-step s (1..T) advances [s*r, dim - s*r) from the previous level; levels in between live in
+    // scratch buffers whose rings are never read
+    const size_t bytes = (size_t)p->st.L * p->st.M * p->st.N * p->spec.esize();
+    for (int i = 0; i < (T > 2 ? 2 : 1); ++i)
+        if (!p->scratch[i] && cudaMalloc(&p->scratch[i], bytes) != cudaSuccess)
+            return fail(DRS_E_CUDA, "cudaMalloc of the temporal scratch buffer failed");
+    const void* src = in;
+    for (int s = 1; s <= T; ++s) {
+        void* dst = s == T ? out : p->scratch[(s - 1) & 1];
+        int rc = launch_one(p, src, dst, stream, s * p->spec.base_order);
+        if (rc != DRS_OK) return rc;
+        src = dst;
+    }
+    return DRS_OK;
+}
+
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring) {
     CUtensorMap* tm = nullptr;
     int rc = tensor_map_for(p, in, &tm);
     if (rc != DRS_OK) return rc;
     DevParams q;
-    fill_params(p, in, out, q);
+    fill_params(p, in, out, q, ring);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
     if (tiles <= 0) return DRS_OK;
     const long long ctas = (tiles + p->spec.nw - 1) / p->spec.nw;
@@ -554,6 +577,7 @@ void drs_plan_destroy(drs_plan* p) {
         cudaFree(p->d_fault);
         cudaFree(p->d_res);
         for (void* b : p->h_dev) if (b) cudaFree(b);
+        for (void* b : p->scratch) if (b) cudaFree(b);
         if (p->mod) driver().ModuleUnload(p->mod);
     }
     delete p;
@@ -699,6 +723,8 @@ int drs_plan_set_slab(drs_plan* p, long long global_slow, long long lo, long lon
     if (!p) return fail(DRS_E_ARG, "null plan");
     const long long ghost = p->spec.halo;
     if (lo < 0 || hi <= lo || hi > global_slow) return fail(DRS_E_ARG, "bad slab range");
+    if (p->spec.sub_launches > 1)
+        return fail(DRS_E_ARG, "slab runs with --step > 1 need --fuse algebraic (multi-launch sub-steps are single-GPU)");
     if (hi - lo + 2 * ghost != p->local_slow())
         return fail(DRS_E_ARG, "slab arrays must hold hi - lo + 2*Halo planes along the slow axis");
     p->slab = true; p->g_slow = global_slow; p->lo = lo; p->hi = hi;

@@ -31,6 +31,11 @@ struct KernelSpec {
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
     int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
     bool tma_ok = true;         // false -> rows not 16-byte multiples: naive kernel does the sweep
+    // 3D `--step n` in temporal mode: n launches of the single-step kernel with frozen rings of
+    // r, 2r, ... n*r through plan-owned scratch buffers (sub-steps exactly as a fused kernel would
+    // evaluate them; not yet fused in one kernel -- no HBM saving, but no 25/35-point operator either)
+    int sub_launches = 1;
+    int base_order = 0;         // Halo of one sub-step
     // row-factorised evaluation (temporal mode only): out = sum_dj w[dj] * H(row j+dj) + residual terms,
     // H(row)(x) = sum_di h[di] * u[row][x+di] computed once per row and reused by every output row
     bool factored = false;
@@ -97,7 +102,12 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     s.gold = comp.terms();
     const int vec = s.vec();
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
-    if (temporal && s.dim == 3) { temporal = false; s.note = "3D temporal blocking not available: composed operator used"; }
+    bool multi3d = false;
+    if (temporal && s.dim == 3) {
+        temporal = false;
+        multi3d = true;
+        s.note = "3D temporal depth runs as one single-step launch per sub-step (not fused in-kernel)";
+    }
     if (temporal) {
         int emax = 0;
         for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
@@ -106,7 +116,9 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
             temporal = false; s.note = "depth leaves no useful columns per warp: composed operator used";
         }
     }
+    s.base_order = order;
     if (temporal) { s.ts = k.step; s.chain = st.base_terms(); }
+    else if (multi3d) { s.ts = 1; s.chain = st.base_terms(); s.sub_launches = k.step; }
     else { s.ts = 1; s.chain = s.gold; s.fuse = k.step > 1 ? DRS_FUSE_ALGEBRAIC : k.fuse; }
     s.rk = s.rj = s.e = 0;
     for (const Term& t : s.chain) {
@@ -125,7 +137,17 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.nw = 2; s.st = 2;
         s.rb = s.dtype == DRS_F64 ? 4 : 8;
         s.vt = s.dtype == DRS_F64 ? 2 : 1;
-        s.chunk = s.dtype == DRS_F64 ? (st.M >= 8192 ? 256 : 128) : (st.M >= 8192 ? 32 : 64);
+        // enough tiles for ~60 (fp64) / ~240 (fp32) warps' worth of work per SM, but chunks long
+        // enough to amortise the pipeline depth
+        const int depth = s.ts == 1 ? 2 * s.rj + 1 : 2 * s.ts * s.rj + s.ts - 1;
+        const int cols_per_warp = 32 * s.vt * vec - 2 * ((((s.ts - 1) * s.e) + vec - 1) / vec * vec);
+        const long long nxs = std::max<long long>(1, (st.N + cols_per_warp - 1) / std::max(1, cols_per_warp));
+        const long long want = 148LL * 60 * (s.dtype == DRS_F64 ? 1 : 4);
+        const long long nys = std::max<long long>(1, (want + nxs - 1) / nxs);
+        long long c = (slow_out + nys - 1) / nys;
+        c = std::max<long long>(c, std::max(64, 16 * depth));
+        c = std::min<long long>(c, 512);
+        s.chunk = (int)((c + 7) / 8 * 8);
     } else {
         s.nw = 2; s.ry = s.rk <= 1 ? 4 : 8; s.chunk = 16;
         s.st = pow2_ceil(2 * s.rk + 2);

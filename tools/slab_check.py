@@ -21,7 +21,7 @@ def main():
         ("3d7pt_star", (64, 40, 128), dict(), 8),
         ("3d7pt_star", (37, 33, 66), dict(sn=5, rows_3d=4), 4),
         ("3d9pt_cross", (48, 24, 64), dict(), 4),
-        ("3d7pt_star", (40, 40, 64), dict(step=2), 8),          # composed operator, ghost = 2
+        ("3d7pt_star", (40, 40, 64), dict(step=2, fuse="algebraic"), 8),   # composed operator, ghost = 2
     ]:
         path = os.path.join(ROOT, "stc", name + ".stc")
         L, M, N = shape
