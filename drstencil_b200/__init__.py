@@ -168,7 +168,7 @@ class Knobs:
     def __init__(self, **kw):
         self.values = dict(_KNOB_DEFAULTS)
         self.explicit = set()
-        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0, vectors=0, no_factor=0)
+        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0, vectors=0, no_factor=0, no_fused3d=0)
         for k, v in kw.items():
             self.set(k, v)
 
@@ -208,7 +208,7 @@ class Knobs:
         k.reserved[3] = self.extra["rows_3d"]
         k.reserved[4] = self.extra["rows_per_stage"]
         k.reserved[5] = self.extra["vectors"]
-        k.reserved[6] = self.extra["no_factor"]
+        k.reserved[6] = (1 if self.extra["no_factor"] else 0) | (2 if self.extra["no_fused3d"] else 0)
         return k
 
     def __repr__(self):

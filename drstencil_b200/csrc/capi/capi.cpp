@@ -322,7 +322,7 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     } else {
         cuuint64_t dims[3] = {(cuuint64_t)p->st.N, (cuuint64_t)p->st.M, (cuuint64_t)p->st.L};
         cuuint64_t strides[2] = {(cuuint64_t)p->st.N * es, (cuuint64_t)p->st.N * (cuuint64_t)p->st.M * es};
-        cuuint32_t box[3] = {(cuuint32_t)s.wb(), (cuuint32_t)(s.ry + 2 * s.rj), 1};
+        cuuint32_t box[3] = {(cuuint32_t)s.wb(), (cuuint32_t)s.box_rows(), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         r = driver().TensorMapEncodeTiled(&m, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -369,7 +369,7 @@ void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int
     if (s.dim == 2) { q.nys = (int)nslow; q.nzs = 1; }
     else {
         const long long yspan = std::max<long long>(0, q.M - 2 * q.halo);
-        q.nys = (int)((yspan + s.ry - 1) / s.ry);
+        q.nys = (int)((yspan + s.tile_rows_useful() - 1) / s.tile_rows_useful());
         q.nzs = (int)nslow;
     }
     q.chunk = s.chunk;
@@ -419,7 +419,7 @@ int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int 
     fill_params(p, in, out, q, ring);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
     if (tiles <= 0) return DRS_OK;
-    const long long ctas = (tiles + p->spec.nw - 1) / p->spec.nw;
+    const long long ctas = (tiles + p->spec.tiles_per_cta() - 1) / p->spec.tiles_per_cta();
     if (ctas > 0x7fffffffLL) return fail(DRS_E_ARG, "grid too large");
     void* args[] = {tm, &q};
     CUresult r = driver().LaunchKernel(p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
@@ -590,12 +590,12 @@ int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
     info->dim = s.dim; info->dtype = s.dtype; info->step = s.step; info->fuse = s.fuse;
     info->L = p->st.L; info->M = p->st.M; info->N = p->st.N;
     info->halo = s.halo; info->npoints = (int)s.chain.size(); info->timesteps_per_sweep = s.step;
-    info->warps_per_cta = s.nw; info->tile_x = s.wu(); info->tile_y = s.dim == 3 ? s.ry : 1;
+    info->warps_per_cta = s.nw; info->tile_x = s.wu(); info->tile_y = s.dim == 3 ? s.tile_rows_useful() : 1;
     info->chunk = s.chunk; info->stages = s.st; info->rows_per_stage = s.dim == 2 ? s.rb : 1;
     DevParams q;
     fill_params(p, nullptr, nullptr, q);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
-    info->grid_x = (int)((tiles + s.nw - 1) / s.nw); info->grid_y = 1; info->grid_z = 1;
+    info->grid_x = (int)((tiles + s.tiles_per_cta() - 1) / s.tiles_per_cta()); info->grid_y = 1; info->grid_z = 1;
     info->block = s.nw * 32;
     info->smem_bytes = s.tma_ok ? s.smem_bytes() : 0;
     info->regs_per_thread = p->regs; info->spill_bytes = p->spill;
@@ -604,7 +604,8 @@ int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
                           (s.dim == 3 ? (double)std::max<long long>(1, q.M - 2 * s.halo) : 1.0);
     double computed;
     if (s.dim == 2) computed = (double)q.nxs * s.wt() * ((double)(q.slow_hi - q.slow_lo) + (double)q.nys * s.ts * (2 * s.rj + 1));
-    else computed = (double)q.nxs * s.wt() * (double)q.nys * s.ry * (double)(q.slow_hi - q.slow_lo);
+    else computed = (double)q.nxs * s.wt() * (double)q.nys * s.tile_rows() *
+                    ((double)(q.slow_hi - q.slow_lo) + (s.fused3d ? (double)q.nzs * (2 * s.ts * s.rk + s.ts - 1) : 0.0));
     info->redundancy = computed / useful;
     std::snprintf(info->kernel_name, sizeof info->kernel_name, "%s%s", s.tma_ok ? "dr_" : "gold_", s.name.c_str());
     return DRS_OK;
@@ -723,8 +724,8 @@ int drs_plan_set_slab(drs_plan* p, long long global_slow, long long lo, long lon
     if (!p) return fail(DRS_E_ARG, "null plan");
     const long long ghost = p->spec.halo;
     if (lo < 0 || hi <= lo || hi > global_slow) return fail(DRS_E_ARG, "bad slab range");
-    if (p->spec.sub_launches > 1)
-        return fail(DRS_E_ARG, "slab runs with --step > 1 need --fuse algebraic (multi-launch sub-steps are single-GPU)");
+    if (p->spec.sub_launches > 1 || p->spec.fused3d)
+        return fail(DRS_E_ARG, "slab runs with --step > 1 need --fuse algebraic (temporal 3D sweeps are single-GPU)");
     if (hi - lo + 2 * ghost != p->local_slow())
         return fail(DRS_E_ARG, "slab arrays must hold hi - lo + 2*Halo planes along the slow axis");
     p->slab = true; p->g_slow = global_slow; p->lo = lo; p->hi = hi;

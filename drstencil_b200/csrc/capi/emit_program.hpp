@@ -65,7 +65,7 @@ static double check_result(const real_t* out, const real_t* ref) {   // common.h
     o << "    p.chunk = " << s.chunk << ";\n";
     o << "    const long long nslow = (p.slow_hi - p.slow_lo + p.chunk - 1) / p.chunk;\n";
     if (s.dim == 2) o << "    p.nys = (int)nslow; p.nzs = 1;\n";
-    else o << "    p.nys = (int)((GridM - 2 * Halo + " << s.ry - 1 << ") / " << s.ry << "); p.nzs = (int)nslow;\n";
+    else o << "    p.nys = (int)((GridM - 2 * Halo + " << s.tile_rows_useful() - 1 << ") / " << s.tile_rows_useful() << "); p.nzs = (int)nslow;\n";
     o << "    return p;\n}\n";
     o << R"(
 static int* g_fault = 0;
@@ -93,7 +93,7 @@ static void gold_launch(const real_t* in, real_t* out) {
         } else {
             o << "    cuuint64_t dims[3] = {(cuuint64_t)GridN, (cuuint64_t)GridM, (cuuint64_t)GridL};\n"
                  "    cuuint64_t strides[2] = {(cuuint64_t)GridN * sizeof(real_t), (cuuint64_t)GridN * GridM * sizeof(real_t)};\n";
-            o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.ry + 2 * s.rj << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
+            o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.box_rows() << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
             o << "    CUresult r = encode(&m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
         }
         o << "        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
@@ -105,7 +105,7 @@ static void gold_launch(const real_t* in, real_t* out) {
              "    if (bases[b] != in) { maps[b] = make_map(in); bases[b] = in; }\n"
              "    drs::Params p = make_params(in, out); p.fault = g_fault;\n"
              "    const long long tiles = (long long)p.nxs * p.nys * p.nzs;\n";
-        o << "    const unsigned ctas = (unsigned)((tiles + " << s.nw - 1 << ") / " << s.nw << ");\n";
+        o << "    const unsigned ctas = (unsigned)((tiles + " << s.tiles_per_cta() - 1 << ") / " << s.tiles_per_cta() << ");\n";
         o << "    drs::TensorMap tm; memcpy(&tm, &maps[b], sizeof tm);\n";
         o << "    DRS_NAME<<<ctas, " << s.nw * 32 << ", " << s.smem_bytes() << ">>>(tm, p);\n}\n";
     } else {

@@ -36,6 +36,8 @@ struct KernelSpec {
     // evaluate them; not yet fused in one kernel -- no HBM saving, but no 25/35-point operator either)
     int sub_launches = 1;
     int base_order = 0;         // Halo of one sub-step
+    // 3D `--step n` fused in one kernel (drs_sweep3d_t.cuh): a CTA of nw warps stacked along y
+    bool fused3d = false;
     // row-factorised evaluation (temporal mode only): out = sum_dj w[dj] * H(row j+dj) + residual terms,
     // H(row)(x) = sum_di h[di] * u[row][x+di] computed once per row and reused by every output row
     bool factored = false;
@@ -52,11 +54,20 @@ struct KernelSpec {
     int hw() const { return ((ts - 1) * e + vec() - 1) / vec() * vec(); }
     int cols() const { return (dim == 2 ? vt : 1) * vec(); }   // consecutive columns per thread
     int wt() const { return 32 * cols(); }
-    int wu() const { return dim == 2 ? wt() - 2 * hw() : wt(); }
+    int wu() const { return (dim == 2 || fused3d) ? wt() - 2 * hw() : wt(); }
     int wb() const { return wt() + 2 * e0(); }
-    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * (ry + 2 * rj) * esize(); }
+    // 3D: rows of one tile (a warp's, or the whole CTA's when fused3d), rows it stores, rows of its TMA box
+    int tile_rows() const { return fused3d ? nw * ry : ry; }
+    int tile_rows_useful() const { return fused3d ? nw * ry - 2 * (ts - 1) * rj : ry; }
+    int box_rows() const { return tile_rows() + 2 * rj; }
+    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * box_rows() * esize(); }
     int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
-    int smem_bytes() const { return nw * st * stage_stride() + nw * st * 8; }
+    int smem_bytes() const {
+        if (fused3d) return (st + 2 * (ts - 1)) * stage_stride() + st * 8;
+        return nw * st * stage_stride() + nw * st * 8;
+    }
+    // tiles handled by one CTA
+    int tiles_per_cta() const { return fused3d ? 1 : nw; }
 };
 
 inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
@@ -102,11 +113,17 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     s.gold = comp.terms();
     const int vec = s.vec();
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
-    bool multi3d = false;
+    bool multi3d = false, fused3d = false;
     if (temporal && s.dim == 3) {
         temporal = false;
-        multi3d = true;
-        s.note = "3D temporal depth runs as one single-step launch per sub-step (not fused in-kernel)";
+        int emax = 0;
+        for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
+        const bool fits = 32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) >= vec && k.step <= 4;
+        if (fits && !(k.reserved[6] & 2)) fused3d = true;
+        else {
+            multi3d = true;
+            s.note = "3D temporal depth runs as one single-step launch per sub-step (not fused in-kernel)";
+        }
     }
     if (temporal) {
         int emax = 0;
@@ -118,6 +135,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     s.base_order = order;
     if (temporal) { s.ts = k.step; s.chain = st.base_terms(); }
+    else if (fused3d) { s.ts = k.step; s.chain = st.base_terms(); s.fused3d = true; }
     else if (multi3d) { s.ts = 1; s.chain = st.base_terms(); s.sub_launches = k.step; }
     else { s.ts = 1; s.chain = s.gold; s.fuse = k.step > 1 ? DRS_FUSE_ALGEBRAIC : k.fuse; }
     s.rk = s.rj = s.e = 0;
@@ -126,7 +144,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.rj = std::max(s.rj, std::abs(t.dj));
         s.e = std::max(s.e, std::abs(t.di));
     }
-    if (s.ts > 1 && k.reserved[6] == 0) factorise_rows(s);
+    if (s.ts > 1 && !(k.reserved[6] & 1)) factorise_rows(s);
     // --- geometry ---
     const long long slow = s.dim == 3 ? st.L : st.M;
     const long long slow_out = std::max<long long>(1, slow - 2 * s.halo);
@@ -148,6 +166,8 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         c = std::max<long long>(c, std::max(64, 16 * depth));
         c = std::min<long long>(c, 512);
         s.chunk = (int)((c + 7) / 8 * 8);
+    } else if (s.fused3d) {
+        s.nw = 8; s.ry = 4; s.st = 2; s.chunk = 32;
     } else {
         s.nw = 2; s.ry = s.rk <= 1 ? 4 : 8; s.chunk = 16;
         s.st = pow2_ceil(2 * s.rk + 2);
@@ -175,17 +195,22 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     {
         // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
         // per SM is the most that budget allows (never forces spills)
-        const int live = s.dim == 3 ? (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4)
+        const int live = s.fused3d ? (s.ts * (2 * s.rk + 1) * s.ry * vec + 16) * (s.esize() / 4)
+                         : s.dim == 3 ? (2 * s.rk + 1) * s.ry * vec * (s.esize() / 4)
                          : s.ts == 1 ? (2 * s.rj + 1) * (s.cols() + 2 * s.e) * (s.esize() / 4)
                                      : (s.ts * (2 * s.rj + 1) * s.cols() + 2 * (s.cols() + 2 * s.e)) * (s.esize() / 4);
         const int est = std::min(255, live + (s.dim == 2 ? 56 : 72));
         s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
     }
     if (k.reserved[1] > 0) s.minb = k.reserved[1];
-    if (s.dim == 3 && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);
+    if (s.dim == 3 && !s.fused3d && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);
+    if (s.fused3d) {
+        while (s.tile_rows_useful() < 1 && s.nw < 16) s.nw *= 2;
+        if (s.tile_rows_useful() < 1) return "temporal depth too large for a 3D tile";
+    }
     if (s.chunk > slow_out) s.chunk = (int)slow_out;
     if (s.chunk < 1) s.chunk = 1;
-    while (s.smem_bytes() > 227 * 1024 && s.nw > 1) s.nw /= 2;
+    while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d) s.nw /= 2;
     while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
     if (s.smem_bytes() > 227 * 1024) return "tile does not fit in shared memory";
     // TMA needs 16-byte row pitch
@@ -308,6 +333,25 @@ inline void emit_scatter(std::ostringstream& o, const KernelSpec& s) {
     o << "\n";
 }
 
+// 3D scatter (drs_sweep3d_t.cuh): P(dk) is the partial sum of the output plane that sees the source
+// plane at k-offset dk; U(dj, di) is the source plane at row/column offsets.
+inline void emit_scatter3(std::ostringstream& o, const KernelSpec& s) {
+    o << "#define DRS_SCATTER3(P, U)";
+    for (int dk = -s.rk; dk <= s.rk; ++dk) {
+        const std::string P = "P(" + std::to_string(dk) + ")";
+        bool started = dk != -s.rk;
+        for (const Term& t : s.chain) {
+            if (t.dk != dk) continue;
+            const std::string U = "U(" + std::to_string(t.dj) + ", " + std::to_string(t.di) + ")";
+            if (!started) o << " \\\n    " << P << " = rmul(" << U << ", (real)(" << lit17(t.coef) << "));";
+            else o << " \\\n    " << P << " = rfma(" << U << ", (real)(" << lit17(t.coef) << "), " << P << ");";
+            started = true;
+        }
+        if (!started) o << " \\\n    " << P << " = (real)0;";
+    }
+    o << "\n";
+}
+
 inline void emit_chain(std::ostringstream& o, const char* macro, const std::vector<Term>& terms) {
     // nvcc contracts t1 + t2 + ... + tP (gold order) into mul(t2), fma(t1), fma(t3) ... fma(tP);
     // the chain is emitted in that order so that results match the reference's gold kernel bit
@@ -346,9 +390,11 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
     emit_chain(o, "DRS_CHAIN", s.chain);
-    if (s.ts > 1) emit_scatter(o, s);
+    if (s.ts > 1 && s.dim == 2) emit_scatter(o, s);
+    if (s.fused3d) emit_scatter3(o, s);
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
-    if (s.tma_ok) o << "#include \"" << (s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
+    if (s.tma_ok)
+        o << "#include \"" << (s.fused3d ? "drs_sweep3d_t.cuh" : s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
     o << "#include \"drs_gold.cuh\"\n";
     return o.str();
 }

@@ -1,0 +1,238 @@
+// drs_sweep3d_t.cuh -- 3D sweep with IN-KERNEL TEMPORAL BLOCKING for sm_100a (`--step n`, n >= 2).
+//
+// The reference realises `--step n` by multiplying the operator out on the host (3d7pt_star ->
+// 25 points at n = 2, /root/reference/drstencil.hpp:262-282) and sweeping that once.  Here n
+// sub-steps of the BASE operator run inside one kernel, so the grid makes one HBM round trip per
+// n timesteps and the work per update stays that of the small operator.
+//
+// Unlike the single-step kernel (drs_sweep3d.cuh, warp-private tiles) the unit of work is a CTA:
+// DRS_NW warps stacked along y share one x-y tile and march along k together.
+//   * level 0 (input) planes arrive through a CTA-wide ring of DRS_ST stages, one TMA box
+//     (cp.async.bulk.tensor.3d, tile + halo) and one mbarrier per plane;
+//   * the sub-steps are evaluated in SCATTER form, as in the 2D temporal kernel: a plane of time
+//     level s-1 is pushed into the partial sums of the 2*RK+1 level-s planes it touches; per-thread
+//     state is `pw[TS][2*RK+1][RY][V]`, rotated statically;
+//   * a completed plane of an intermediate level is published to a shared-memory plane buffer
+//     (double-buffered by iteration parity) from which every warp -- the owner included -- reads it
+//     back with its x/y neighbours in the next iteration; one __syncthreads per plane orders
+//     publication, consumption and the hand-back of the TMA stage;
+//   * levels are evaluated top-down inside an iteration, so their chains are independent and the
+//     wait for the newest input plane comes last;
+//   * the tile loses RJ rows / E columns per level at its edges (overlapped tiling): a CTA of
+//     TY = NW*RY rows stores TY - 2*(TS-1)*RJ of them.
+// Results equal the composed operator up to rounding (<= 1e-12 relative, tests), the frozen ring of
+// width n*r is never written.
+//
+// Generated translation unit must define: DRS_T DRS_NAME DRS_RK DRS_RJ DRS_E DRS_TS DRS_NW DRS_RY
+// DRS_ST DRS_MINB DRS_SCATTER3(P,U).
+#pragma once
+#include "drs_common.cuh"
+
+namespace drs {
+namespace s3t {
+
+constexpr int RK = DRS_RK, RJ = DRS_RJ, E = DRS_E, TS = DRS_TS;
+constexpr int K2 = 2 * RK + 1;
+constexpr int RY = DRS_RY, NW = DRS_NW, ST = DRS_ST;
+constexpr int E0 = ((E + kVec - 1) / kVec) * kVec;
+constexpr int HW = (((TS - 1) * E + kVec - 1) / kVec) * kVec;   // columns lost per side
+constexpr int HY = (TS - 1) * RJ;                               // rows lost per side
+constexpr int WT = 32 * kVec, WU = WT - 2 * HW, WB = WT + 2 * E0;
+constexpr int TY = NW * RY, TYU = TY - 2 * HY, YB = TY + 2 * RJ;
+constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);
+constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128;
+constexpr int NLV = TS - 1;                                     // intermediate levels kept in shared memory
+constexpr int DEPTH = 2 * TS * RK + TS - 1;
+constexpr int UH = RY + 2 * RJ, UW = kVec + 2 * E;
+static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
+static_assert(TS >= 2, "single-step sweeps use drs_sweep3d.cuh");
+static_assert(WU > 0 && TYU > 0, "tile too small for this depth");
+
+__device__ __forceinline__ constexpr int mod_k2(int v) { return ((v % K2) + K2) % K2; }
+
+struct Ctx {
+    unsigned char* ring;     // ST input planes
+    unsigned char* lv;       // NLV x 2 published planes
+    drs_u64* bars;
+    const TensorMap* tmap;
+    int* fault;
+    int x_box, y_box, z0;    // TMA coordinates of iteration 0
+    int NIT;
+    int warp, lane;
+    // output
+    int x_first, v_lo, v_hi;
+    int y_first;             // global row of this warp's tile row 0
+    int y_lo, y_hi;          // storable tile rows of this warp: y_lo <= y < y_hi
+    drs_i64 z_out0;
+    int n_first, n_end;
+    drs_i64 M, N;
+    real* out;
+    __device__ __forceinline__ void issue(int n) const {
+        const int s = n & (ST - 1);
+        mbar_expect_tx(&bars[s], PLANE_BYTES);
+        tma_load_3d(ring + s * PLANE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
+    }
+};
+
+template <int PH>
+__device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ctx& c, int n) {
+#pragma unroll
+    for (int s = TS; s >= 1; --s) {
+        // ---- source plane of level s-1 as this thread sees it: own rows/columns + neighbours ----
+        const real* src;
+        if (s == 1) {
+            if (!mbar_wait(&c.bars[n & (ST - 1)], (drs_u32)((n / ST) & 1), c.fault)) return false;
+            src = reinterpret_cast<const real*>(c.ring + (n & (ST - 1)) * PLANE_STRIDE);
+        } else {
+            src = reinterpret_cast<const real*>(c.lv + ((s >= 2 ? s - 2 : 0) * 2 + ((n + 1) & 1)) * PLANE_STRIDE);
+        }
+        const real* mine = src + (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;   // tile row 0, element 0
+        // ---- scatter into the partial sums of level s ----
+#pragma unroll
+        for (int y = 0; y < RY; ++y) {
+#pragma unroll
+            for (int v = 0; v < kVec; ++v) {
+#define DRS_U_(dj, di) mine[(y + (dj)) * WB + v + (di)]
+#define DRS_P_(dk) pw[s - 1][mod_k2(PH - (dk))][y][v]
+                DRS_SCATTER3(DRS_P_, DRS_U_)
+#undef DRS_U_
+#undef DRS_P_
+            }
+        }
+        // ---- the plane of level s completed by this iteration ----
+        if (s < TS) {
+            real* dst = reinterpret_cast<real*>(c.lv + ((s - 1) * 2 + (n & 1)) * PLANE_STRIDE) +
+                        (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;
+#pragma unroll
+            for (int y = 0; y < RY; ++y) {
+                real o[kVec];
+#pragma unroll
+                for (int v = 0; v < kVec; ++v) o[v] = pw[s < TS ? s - 1 : 0][mod_k2(PH - RK)][y][v];
+                if constexpr (sizeof(real) == 8) *reinterpret_cast<double2*>(dst + y * WB) = make_double2(o[0], o[1]);
+                else *reinterpret_cast<float4*>(dst + y * WB) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        } else if (n >= c.n_first && n < c.n_end) {
+            real* orow = c.out + ((c.z_out0 + n) * c.M + c.y_first) * c.N + c.x_first;
+#pragma unroll
+            for (int y = 0; y < RY; ++y) {
+                if (y >= c.y_lo && y < c.y_hi) {
+                    real o[kVec];
+#pragma unroll
+                    for (int v = 0; v < kVec; ++v) o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
+                    real* dst = orow + (drs_i64)y * c.N;
+                    if (c.v_lo <= 0 && c.v_hi >= kVec) {
+                        stg_vec(dst, o);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < kVec; ++v)
+                            if (v >= c.v_lo && v < c.v_hi) dst[v] = o[v];
+                    }
+                }
+            }
+        }
+    }
+    // published planes visible to every warp; the input stage is consumed by all of them
+    __syncthreads();
+    if (threadIdx.x == 0 && n + ST < c.NIT) {
+        fence_proxy_async();
+        c.issue(n + ST);
+    }
+    return true;
+}
+
+template <int PH>
+__device__ __forceinline__ bool phases(real (&pw)[TS][K2][RY][kVec], const Ctx& c, int n0) {
+    if constexpr (PH < K2) {
+        if (!iteration<PH>(pw, c, n0 + PH)) return false;
+        return phases<PH + 1>(pw, c, n0);
+    } else {
+        return true;
+    }
+}
+
+__device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Ctx c;
+    c.warp = threadIdx.x >> 5;
+    c.lane = threadIdx.x & 31;
+    c.ring = smem_raw;
+    c.lv = smem_raw + ST * PLANE_STRIDE;
+    c.bars = reinterpret_cast<drs_u64*>(smem_raw + (ST + 2 * NLV) * PLANE_STRIDE);
+    c.tmap = &tmap;
+    c.fault = p.fault;
+
+    const drs_i64 tile = blockIdx.x;
+    const drs_i64 per_chunk = (drs_i64)p.nxs * p.nys;
+    const int zc = (int)(tile / per_chunk);
+    const int rem = (int)(tile % per_chunk);
+    const int cy = rem / p.nxs, cx = rem % p.nxs;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) mbar_init(&c.bars[s], 1);
+        fence_mbar_init();
+        fence_proxy_async();
+    }
+    // the published-plane buffers start out zeroed so that never-written halo cells are finite
+    for (int x = threadIdx.x; x < 2 * NLV * PLANE_STRIDE / 16; x += blockDim.x)
+        reinterpret_cast<uint4*>(c.lv)[x] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+
+    const int H = p.halo;
+    const int X0 = (H / kVec) * kVec + cx * WU - HW;
+    const int Y0 = H + cy * TYU - HY;
+    const drs_i64 za = p.slow_lo + (drs_i64)zc * p.chunk;
+    const drs_i64 zb = (za + p.chunk < p.slow_hi) ? za + p.chunk : p.slow_hi;
+    const int n_end = (int)(zb - za) + DEPTH;
+    c.NIT = (n_end + K2 - 1) / K2 * K2;
+    c.z0 = (int)(za - TS * RK);
+    c.x_box = X0 - E0;
+    c.y_box = Y0 - RJ;
+    c.x_first = X0 + c.lane * kVec;
+    {
+        const drs_i64 lo = (H > X0 + HW) ? H : X0 + HW;
+        const drs_i64 hi = (p.N - H < X0 + HW + WU) ? p.N - H : X0 + HW + WU;
+        c.v_lo = (int)(lo - c.x_first);
+        c.v_hi = (int)(hi - c.x_first);
+    }
+    c.y_first = Y0 + c.warp * RY;
+    {
+        const drs_i64 lo = (H > Y0 + HY) ? H : Y0 + HY;
+        const drs_i64 hi = (p.M - H < Y0 + HY + TYU) ? p.M - H : Y0 + HY + TYU;
+        c.y_lo = (int)(lo - c.y_first);
+        c.y_hi = (int)(hi - c.y_first);
+    }
+    c.n_first = DEPTH;
+    c.n_end = n_end;
+    c.z_out0 = za - DEPTH;
+    c.M = p.M;
+    c.N = p.N;
+    c.out = p.out;
+
+    if (threadIdx.x == 0) {
+        for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
+    }
+
+    real pw[TS][K2][RY][kVec];
+#pragma unroll
+    for (int s = 0; s < TS; ++s)
+#pragma unroll
+        for (int d = 0; d < K2; ++d)
+#pragma unroll
+            for (int y = 0; y < RY; ++y)
+#pragma unroll
+                for (int v = 0; v < kVec; ++v) pw[s][d][y][v] = (real)0;
+
+#pragma unroll 1
+    for (int n0 = 0; n0 < c.NIT; n0 += K2) {
+        if (!phases<0>(pw, c, n0)) break;
+    }
+}
+
+}  // namespace s3t
+}  // namespace drs
+
+extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
+DRS_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
+    drs::s3t::sweep(tmap, p);
+}

@@ -342,19 +342,25 @@ def test_fp32_temporal_all_shapes(built, name):
     assert max_rel(A.cpu().numpy()[inner], ref64[inner]) <= 1e-5
 
 
-@pytest.mark.parametrize("name,step", [("3d7pt_star", 2), ("3d7pt_star", 3), ("3d9pt_cross", 2)])
-def test_3d_temporal_depth_by_sub_launches(built, name, step):
-    """3D `--step n` (temporal): n single-step launches with rings r, 2r, .. n*r through scratch
-    buffers == the composed operator within 1e-12, frozen ring of width n*r untouched."""
+@pytest.mark.parametrize("name,step,kn", [
+    ("3d7pt_star", 2, dict()), ("3d7pt_star", 3, dict()), ("3d9pt_cross", 2, dict()),
+    ("3d7pt_star", 2, dict(warps=4, sn=7)), ("3d7pt_star", 4, dict(warps=8, rows_3d=2, sn=9, stages=4)),
+    ("3d7pt_star", 2, dict(no_fused3d=1)), ("3d9pt_cross", 3, dict(no_fused3d=1)),
+])
+def test_3d_temporal_depth(built, name, step, kn):
+    """3D `--step n` (temporal): n sub-steps fused in one kernel (drs_sweep3d_t.cuh), or -- with the
+    engine override no_fused3d -- n single-step launches through scratch buffers.  Either way ==
+    the composed operator within 1e-12, and the frozen ring of width n*r is untouched."""
     from oracle import oracle
-    for shape in [(40, 48, 72), (23, 17, 130)]:
-        plan = _plan(name, shape, step=step)
-        assert "sub-step" in plan.note
+    for shape in [(40, 48, 72), (23, 37, 130), (9 + 2 * step, 70, 64)]:
+        plan = _plan(name, shape, step=step, **kn)
+        fused = not kn.get("no_fused3d")
+        assert ("drs_sweep3d_t.cuh" in plan.source) == fused
         a0 = oracle.rand_array(shape)
         A, B = _dev(a0), _dev(np.full(shape, -9.0))
         n = plan.run(A, B, iterations=2 * step)
         plan.sync_check()
-        assert n == 2 and plan.launch_count == 2 * step
+        assert n == 2 and plan.launch_count == (2 if fused else 2 * step)
         refA, refB = a0.copy(), np.full(shape, -9.0)
         offs, coefs, halo = oracle_terms(name, step)
         oracle.sweep(refA, refB, offs, coefs, halo)
@@ -362,7 +368,7 @@ def test_3d_temporal_depth_by_sub_launches(built, name, step):
         assert halo == plan.halo
         inner = tuple(slice(halo, -halo) for _ in shape)
         got = A.cpu().numpy()
-        assert max_rel(got[inner], refA[inner]) <= 1e-12
+        assert max_rel(got[inner], refA[inner]) <= 1e-12, (name, step, shape, kn)
         ring = np.ones(shape, bool)
         ring[inner] = False
         assert np.array_equal(got[ring], refA[ring])

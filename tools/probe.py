@@ -56,10 +56,12 @@ def main():
     variants = {
         "c1": [dict(sn=256, warps=1, min_blocks=16)],
         "c2": [dict(step=4, sn=256, vectors=2, stages=2)],
-        "c3": [dict(dtype="f32", sn=64)],
-        "c4": [dict(sn=16, rows_3d=4), dict(sn=16, rows_3d=8), dict(sn=16, rows_3d=6), dict(sn=16, rows_3d=12, warps=1)],
-        "c5": [dict(sn=16, rows_3d=4), dict(sn=16, rows_3d=8), dict(sn=8, rows_3d=8), dict(sn=32, rows_3d=8), dict(sn=16, rows_3d=8, warps=4),
-               dict(sn=16, rows_3d=8, warps=1), dict(sn=16, rows_3d=6), dict(sn=16, rows_3d=8, stages=8)],
+        "c3": [dict(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)],
+        "c4": [dict(sn=16, rows_3d=4), dict(step=2), dict(step=2, sn=64), dict(step=2, sn=128), dict(step=2, sn=64, min_blocks=2),
+               dict(step=2, sn=64, warps=4), dict(step=2, sn=64, warps=4, min_blocks=3), dict(step=2, sn=64, stages=4),
+               dict(step=2, sn=64, warps=16, rows_3d=2), dict(step=2, sn=64, warps=8, rows_3d=2, min_blocks=2),
+               dict(step=3, sn=64), dict(step=3, sn=96, warps=16, rows_3d=2), dict(step=2, no_fused3d=1)],
+        "c5": [dict(sn=16, rows_3d=6)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
