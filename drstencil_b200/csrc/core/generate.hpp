@@ -167,7 +167,9 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         c = std::min<long long>(c, 512);
         s.chunk = (int)((c + 7) / 8 * 8);
     } else if (s.fused3d) {
-        s.nw = 8; s.ry = 4; s.st = 2; s.chunk = 32;
+        // probe on B200 (profiles/): 8 warps x 4 rows, two CTAs per SM, long chunks
+        if (s.ts == 2) { s.nw = 8; s.ry = 4; } else { s.nw = 16; s.ry = 2; }
+        s.st = 2; s.chunk = 128;
     } else {
         s.nw = 2; s.ry = s.rk <= 1 ? 4 : 8; s.chunk = 16;
         s.st = pow2_ceil(2 * s.rk + 2);
@@ -201,6 +203,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
                                      : (s.ts * (2 * s.rj + 1) * s.cols() + 2 * (s.cols() + 2 * s.e)) * (s.esize() / 4);
         const int est = std::min(255, live + (s.dim == 2 ? 56 : 72));
         s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
+        if (s.fused3d && s.nw * 32 <= 256) s.minb = std::max(s.minb, 2);   // 128 registers: no spills measured
     }
     if (k.reserved[1] > 0) s.minb = k.reserved[1];
     if (s.dim == 3 && !s.fused3d && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);

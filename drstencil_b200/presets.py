@@ -30,4 +30,6 @@ PRESETS = {
     "c3": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)),
     "c4": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(sn=16, rows_3d=4)),
     "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(sn=16, rows_3d=6)),
+    # extra (not a BASELINE.json config): c4 with in-kernel temporal depth 2
+    "c4t2": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(step=2)),
 }
