@@ -125,11 +125,15 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
             s.note = "3D temporal depth runs as one single-step launch per sub-step (not fused in-kernel)";
         }
     }
+    int need_vt = 1;      // a level's x neighbours come from the adjacent lane: E <= columns per thread
     if (temporal) {
         int emax = 0;
         for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
-        if (emax > vec) { temporal = false; s.note = "x extent exceeds one vector: composed operator used"; }
-        else if (32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) < vec) {   // (vt = 1 worst case)
+        if (emax > vec) need_vt = 2;
+        const int cols = need_vt * vec;
+        if (emax > cols || 32 * cols + 2 * ((emax + vec - 1) / vec * vec) > 256) {
+            temporal = false; s.note = "x extent exceeds what one lane can hand its neighbour: composed operator used";
+        } else if (32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) < vec) {   // (vt = 1 worst case)
             temporal = false; s.note = "depth leaves no useful columns per warp: composed operator used";
         }
     }
@@ -184,6 +188,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     if (knob_given(k, KB_PREFETCH) && k.prefetch) s.st = std::max(s.st, 8);
     if (s.dim == 2 && knob_given(k, KB_BMX) && k.block_merge_x >= 1) s.vt = std::min(2, k.block_merge_x);
     if (k.reserved[5] > 0 && s.dim == 2) s.vt = std::min(2, k.reserved[5]);
+    if (s.dim == 2 && s.vt < need_vt && s.ts > 1) s.vt = need_vt;
     if (s.dim == 2 && s.wb() > 256) s.vt = 1;   // a TMA box is at most 256 elements wide
     if (s.dim == 3) {
         const int my = std::max(k.block_merge_y, k.cyclic_merge_y);
