@@ -113,6 +113,28 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     s.gold = comp.terms();
     const int vec = s.vec();
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
+    if (temporal) {
+        // The reference multiplies the operator out and prints the result with 6 significant digits
+        // (drstencil_2d.hpp:174).  Sub-steps of the base operator reproduce that only if no composed
+        // coefficient loses digits on the way; otherwise parity comes first: the composed operator is
+        // evaluated literally unless temporal mode was asked for explicitly.
+        double worst = 0;
+        for (const auto& [p, c] : comp.points)
+            if (c != 0.0) worst = std::max(worst, std::fabs(coef_literal_value(c) - c) / std::fabs(c));
+        if (worst > 1e-13) {
+            char b[160];
+            if (knob_given(k, KB_FUSE)) {
+                std::snprintf(b, sizeof b, "composed coefficients change by up to %.1e when printed with 6 digits: temporal "
+                              "sub-steps follow the exact operator, not the reference's literals", worst);
+                s.note = b;
+            } else {
+                std::snprintf(b, sizeof b, "composed coefficients change by up to %.1e when printed with 6 digits: composed "
+                              "operator used for parity (--fuse temporal overrides)", worst);
+                s.note = b;
+                temporal = false;
+            }
+        }
+    }
     bool multi3d = false, fused3d = false;
     if (temporal && s.dim == 3) {
         temporal = false;
