@@ -208,6 +208,9 @@ def run_single(args, rank, world):
     wl = args.workload or "c5"
     preset, timesteps, desc = WORKLOADS[wl]
     path, kn = PRESETS[preset]
+    if wl == "c5" and args.depth > 1:
+        kn = drs.Knobs(step=args.depth)
+        desc += " [temporal depth %d]" % args.depth
     st = drs.Stencil.from_file(path)
     plan = drs.Plan(st, kn)
     shape = st.shape
@@ -380,6 +383,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip per_config / cpu_baseline (profiling runs)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo exchange path")
+    ap.add_argument("--depth", type=int, default=1, help="c5 only: in-kernel temporal depth (extra evidence; "
+                    "the contract line is depth 1, bit-exact)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -724,8 +724,8 @@ int drs_plan_set_slab(drs_plan* p, long long global_slow, long long lo, long lon
     if (!p) return fail(DRS_E_ARG, "null plan");
     const long long ghost = p->spec.halo;
     if (lo < 0 || hi <= lo || hi > global_slow) return fail(DRS_E_ARG, "bad slab range");
-    if (p->spec.sub_launches > 1 || p->spec.fused3d)
-        return fail(DRS_E_ARG, "slab runs with --step > 1 need --fuse algebraic (temporal 3D sweeps are single-GPU)");
+    if (p->spec.sub_launches > 1)
+        return fail(DRS_E_ARG, "slab runs cannot use per-sub-step launches: use the fused temporal kernel or --fuse algebraic");
     if (hi - lo + 2 * ghost != p->local_slow())
         return fail(DRS_E_ARG, "slab arrays must hold hi - lo + 2*Halo planes along the slow axis");
     p->slab = true; p->g_slow = global_slow; p->lo = lo; p->hi = hi;

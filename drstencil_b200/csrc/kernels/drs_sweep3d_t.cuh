@@ -20,6 +20,8 @@
 //     wait for the newest input plane comes last;
 //   * the tile loses RJ rows / E columns per level at its edges (overlapped tiling): a CTA of
 //     TY = NW*RY rows stores TY - 2*(TS-1)*RJ of them.
+//   * slab mode: like the single-step kernel, boundary output planes are stored a second time into
+//     the neighbour GPUs' ghost planes (n*r of them per side).
 // Results equal the composed operator up to rounding (<= 1e-12 relative, tests), the frozen ring of
 // width n*r is never written.
 //
@@ -67,6 +69,9 @@ struct Ctx {
     int n_first, n_end;
     drs_i64 M, N;
     real* out;
+    // slab mode: boundary output planes are also stored into the neighbours' ghost planes (NVLink)
+    real* peer_lo; real* peer_hi;
+    drs_i64 lo0, lo1, lo_shift, hi0, hi1, hi_shift;
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
         mbar_expect_tx(&bars[s], PLANE_BYTES);
@@ -112,20 +117,32 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
                 else *reinterpret_cast<float4*>(dst + y * WB) = make_float4(o[0], o[1], o[2], o[3]);
             }
         } else if (n >= c.n_first && n < c.n_end) {
-            real* orow = c.out + ((c.z_out0 + n) * c.M + c.y_first) * c.N + c.x_first;
+            const drs_i64 z = c.z_out0 + n;
+            const drs_i64 row0 = c.y_first * c.N + c.x_first;
+            real* orow = c.out + z * c.M * c.N + row0;
+            const bool push_lo = c.peer_lo != nullptr && z >= c.lo0 && z < c.lo1;
+            const bool push_hi = c.peer_hi != nullptr && z >= c.hi0 && z < c.hi1;
+            real* plo = push_lo ? c.peer_lo + (z + c.lo_shift) * c.M * c.N + row0 : nullptr;
+            real* phi = push_hi ? c.peer_hi + (z + c.hi_shift) * c.M * c.N + row0 : nullptr;
 #pragma unroll
             for (int y = 0; y < RY; ++y) {
                 if (y >= c.y_lo && y < c.y_hi) {
                     real o[kVec];
 #pragma unroll
                     for (int v = 0; v < kVec; ++v) o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
-                    real* dst = orow + (drs_i64)y * c.N;
+                    const drs_i64 off = (drs_i64)y * c.N;
                     if (c.v_lo <= 0 && c.v_hi >= kVec) {
-                        stg_vec(dst, o);
+                        stg_vec(orow + off, o);
+                        if (push_lo) stg_vec(plo + off, o);
+                        if (push_hi) stg_vec(phi + off, o);
                     } else {
 #pragma unroll
                         for (int v = 0; v < kVec; ++v)
-                            if (v >= c.v_lo && v < c.v_hi) dst[v] = o[v];
+                            if (v >= c.v_lo && v < c.v_hi) {
+                                orow[off + v] = o[v];
+                                if (push_lo) plo[off + v] = o[v];
+                                if (push_hi) phi[off + v] = o[v];
+                            }
                     }
                 }
             }
@@ -208,6 +225,10 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.M = p.M;
     c.N = p.N;
     c.out = p.out;
+    c.peer_lo = p.peer_lo;
+    c.peer_hi = p.peer_hi;
+    c.lo0 = p.push_lo0; c.lo1 = p.push_lo1; c.lo_shift = p.peer_lo_shift;
+    c.hi0 = p.push_hi0; c.hi1 = p.push_hi1; c.hi_shift = p.peer_hi_shift;
 
     if (threadIdx.x == 0) {
         for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);

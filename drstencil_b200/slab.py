@@ -273,6 +273,10 @@ def bench_slab(args, rank, world, workload, peak_info):
     from .presets import PRESETS
     preset, timesteps, desc = workload
     path, kn = PRESETS[preset]
+    if getattr(args, "depth", 1) > 1:
+        from . import Knobs
+        kn = Knobs(step=args.depth)
+        desc += " [temporal depth %d]" % args.depth
     slab = GpuSlab(path, kn, rank, world, halo=args.halo)
     L, M, N = slab.global_shape
     g = torch.Generator(device="cuda")

@@ -22,6 +22,8 @@ def main():
         ("3d7pt_star", (37, 33, 66), dict(sn=5, rows_3d=4), 4),
         ("3d9pt_cross", (48, 24, 64), dict(), 4),
         ("3d7pt_star", (40, 40, 64), dict(step=2, fuse="algebraic"), 8),   # composed operator, ghost = 2
+        ("3d7pt_star", (56, 44, 130), dict(step=2, sn=9), 8),              # fused temporal kernel, ghost = 2
+        ("3d9pt_cross", (60, 40, 64), dict(step=2), 8),
     ]:
         path = os.path.join(ROOT, "stc", name + ".stc")
         L, M, N = shape
