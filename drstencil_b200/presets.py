@@ -32,4 +32,5 @@ PRESETS = {
     "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(sn=16, rows_3d=6)),
     # extra (not a BASELINE.json config): c4 with in-kernel temporal depth 2
     "c4t2": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(step=2)),
+    "c5t2": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(step=2)),
 }
