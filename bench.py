@@ -410,6 +410,8 @@ def main():
         line = slab.bench_slab(args, rank, world, WORKLOADS["c5"], measured_peak())
     else:
         line, plan = run_single(args, rank, world)
+        del plan                     # frees the device pair drs_run_host allocated
+        torch.cuda.empty_cache()
     if rank == 0:
         if world == 1 and not args.no_extras:
             line["per_config"] = per_config(args)
