@@ -189,7 +189,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         const long long want = 148LL * 60 * (s.dtype == DRS_F64 ? 1 : 4);
         const long long nys = std::max<long long>(1, (want + nxs - 1) / nxs);
         long long c = (slow_out + nys - 1) / nys;
-        c = std::max<long long>(c, std::max(64, 16 * depth));
+        c = std::max<long long>(c, std::max(s.dtype == DRS_F64 ? 128 : 64, 16 * depth));   // per-tile start-up cost
         c = std::min<long long>(c, 512);
         s.chunk = (int)((c + 7) / 8 * 8);
     } else if (s.fused3d) {

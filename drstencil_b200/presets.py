@@ -25,7 +25,7 @@ PRESETS = {
     "3d7pt_star": (_p("3d7pt_star.stc"), Knobs()),
     "3d9pt_cross": (_p("3d9pt_cross.stc"), Knobs()),
     # BASELINE.json configs
-    "c1": (_p("baseline", "c1_2d5pt_star.stc"), Knobs(sn=256, warps=1, min_blocks=16)),
+    "c1": (_p("baseline", "c1_2d5pt_star.stc"), Knobs(sn=128, warps=2, vectors=2, stages=2, rows_per_stage=4)),
     "c2": (_p("baseline", "c2_2d9pt_box.stc"), Knobs(step=4, sn=256, vectors=2, stages=2)),
     "c3": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)),
     "c4": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(sn=16, rows_3d=4)),

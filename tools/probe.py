@@ -54,15 +54,9 @@ def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     out = []
     variants = {
-        "c4": [dict(step=2, sn=64, min_blocks=2), dict(step=2, sn=128, min_blocks=2), dict(step=2, sn=256, min_blocks=2),
-               dict(step=2, sn=128, warps=4, min_blocks=4), dict(step=2, sn=128, warps=4, min_blocks=3),
-               dict(step=2, sn=128, warps=8, rows_3d=2, min_blocks=4), dict(step=2, sn=128, warps=16, rows_3d=2, min_blocks=2),
-               dict(step=2, sn=128, warps=6, min_blocks=3), dict(step=2, sn=128, warps=8, rows_3d=3, min_blocks=2),
-               dict(step=2, sn=128, warps=12, rows_3d=3, min_blocks=1),
-               dict(step=3, sn=128, min_blocks=2), dict(step=3, sn=128, warps=8, rows_3d=2, min_blocks=3),
-               dict(step=3, sn=128, warps=16, rows_3d=2, min_blocks=1), dict(step=3, sn=128, warps=12, rows_3d=2, min_blocks=2),
-               dict(step=4, sn=128, warps=16, rows_3d=2, min_blocks=1)],
-        "c5": [dict(step=2, sn=128, min_blocks=2)],
+        "c1": [dict(sn=128, warps=2, vectors=2, stages=2, rows_per_stage=4), dict(sn=256, warps=1, min_blocks=16, vectors=1, stages=4),
+               dict(sn=128, warps=2, vectors=1, stages=2), dict(sn=64, warps=2, vectors=2, stages=2), dict(sn=128, warps=4, vectors=2, stages=2),
+               dict(sn=128, warps=2, vectors=2, stages=4), dict()],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
