@@ -131,14 +131,6 @@ def time_steps(plan, A, B, timesteps, steps, warmup):
     return e0.elapsed_time(e1) * 1e-3, plan.launch_count - l0
 
 
-def renorm(A):
-    """Keeps the synthetic field finite over many steps (sum of coefficients > 1)."""
-    import torch
-    m = float(A.abs().max())
-    if m > 1e100 or (A.dtype == torch.float32 and m > 1e20):
-        A.mul_(1.0 / m)
-
-
 def cpu_baseline(workload, budget_s=12.0):
     """The oracle port on all host cores over a bounded sample of the workload."""
     import numpy as np

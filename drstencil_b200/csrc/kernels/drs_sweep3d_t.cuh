@@ -45,7 +45,6 @@ constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);
 constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128;
 constexpr int NLV = TS - 1;                                     // intermediate levels kept in shared memory
 constexpr int DEPTH = 2 * TS * RK + TS - 1;
-constexpr int UH = RY + 2 * RJ, UW = kVec + 2 * E;
 static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
 static_assert(TS >= 2, "single-step sweeps use drs_sweep3d.cuh");
 static_assert(WU > 0 && TYU > 0, "tile too small for this depth");

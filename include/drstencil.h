@@ -60,6 +60,10 @@ typedef struct drs_knobs {
     int fuse;          /* --fuse temporal|algebraic   DRS_FUSE_TEMPORAL */
     int explicit_mask; /* bit i set: knob i (in the order above, step = bit 0) was given explicitly;
                           knobs not given explicitly are chosen by the engine's B200 heuristics */
+    /* engine-only tile overrides (0 = let the engine choose); the tuner's extra axes:
+     * [0] ring stages  [1] __launch_bounds__ minimum blocks per SM  [2] warps per CTA
+     * [3] rows per thread in 3D  [4] rows per TMA stage in 2D  [5] 128-bit vectors per thread in 2D
+     * [6] bit 0: no row factorisation, bit 1: 3D temporal depth as per-sub-step launches instead of the fused kernel */
     int reserved[7];
 } drs_knobs;
 

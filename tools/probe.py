@@ -54,9 +54,10 @@ def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     out = []
     variants = {
-        "c1": [dict(sn=128, warps=2, vectors=2, stages=2, rows_per_stage=4), dict(sn=256, warps=1, min_blocks=16, vectors=1, stages=4),
-               dict(sn=128, warps=2, vectors=1, stages=2), dict(sn=64, warps=2, vectors=2, stages=2), dict(sn=128, warps=4, vectors=2, stages=2),
-               dict(sn=128, warps=2, vectors=2, stages=4), dict()],
+        "c1": [dict(sn=128, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=2, stages=2), dict(sn=56, warps=2, vectors=2, stages=2),
+               dict(sn=112, warps=2, vectors=2, stages=2), dict(sn=111, warps=1, vectors=2, stages=2), dict(sn=111, warps=4, vectors=2, stages=2),
+               dict(sn=110, warps=2, vectors=2, stages=2), dict(sn=148, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=1, stages=2),
+               dict(sn=222, warps=1, vectors=2, stages=2), dict(sn=222, warps=2, vectors=1, stages=2)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
