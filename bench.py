@@ -383,11 +383,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 from C (NCCL prints its
+    # version there) are sent to stderr instead
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         line = run_reference(args, rank)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            print(json.dumps(line), file=json_out, flush=True)
         return
 
     import torch
@@ -410,7 +415,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args.workload or "c5")
             refs = {w: reference_gpu_kernel(w) for w in ("c1", "c2", "c4")}
             line["reference_gpu_kernels"] = {w: r for w, r in refs.items() if r}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
