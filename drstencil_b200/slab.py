@@ -280,10 +280,11 @@ def bench_slab(args, rank, world, workload, peak_info):
     slab = GpuSlab(path, kn, rank, world, halo=args.halo)
     L, M, N = slab.global_shape
     g = torch.Generator(device="cuda")
+    dtype = slab.dtype
 
     def plane(zg):
         g.manual_seed(1234 + zg)
-        return torch.rand((M, N), dtype=slab.dtype, device="cuda", generator=g) * 1e-100
+        return torch.rand((M, N), dtype=dtype, device="cuda", generator=g) * 1e-100
 
     slab.fill(plane)
     info = slab.plan.info
