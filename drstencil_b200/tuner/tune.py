@@ -49,7 +49,9 @@ def time_config(st, cfg: Config, sweeps=6, warm=2):
 
 
 def tune(stc, is3d=None, step=1, dtype="f64", fuse="temporal", size=None, budget_s=120.0, top=3, use_ncu=False,
-         peak_gbs=6553.6, log=print):
+         peak_gbs=6553.6, log=print, resume_from=None):
+    """`resume_from`: a previous result file for the same problem -- configurations already timed
+    there are not run again (the reference's tuner always restarts from scratch)."""
     st = Stencil.from_file(stc, is3d)
     if size:
         st.set_size(size)
@@ -62,10 +64,25 @@ def tune(stc, is3d=None, step=1, dtype="f64", fuse="temporal", size=None, budget
     for n in shape:
         npts *= n
     results = []
+    known = {}
+    if resume_from and os.path.exists(resume_from):
+        try:
+            old = json.load(open(resume_from))
+            if old.get("stencil") == os.path.basename(stc) and old.get("shape") == list(shape) and \
+                    (old.get("step"), old.get("dtype"), old.get("fuse")) == (step, dtype, fuse):
+                known = {r["name"]: r for r in old.get("all", [])}
+                log("resuming: %d configurations already measured" % len(known))
+        except (ValueError, KeyError):
+            known = {}
     t0 = time.time()
     best = None
     with open("duration.log", "a") as dl:
         for n, cfg in enumerate(space):
+            if cfg_to_string(cfg) in known:
+                r = dict(known[cfg_to_string(cfg)])
+                r["cfg"] = cfg
+                results.append(r)
+                continue
             if time.time() - t0 > budget_s:
                 log("budget exhausted after %d of %d" % (n, len(space)))
                 break
@@ -122,8 +139,10 @@ def main():
     ap.add_argument("--top", type=int, default=3)
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--out", default="tuning_result.json")
+    ap.add_argument("--resume", action="store_true", help="skip configurations already present in --out")
     a = ap.parse_args()
-    res = tune(a.stc, a.is3d or None, a.step, a.dtype, a.fuse, a.size, a.budget_s, a.top, a.ncu)
+    res = tune(a.stc, a.is3d or None, a.step, a.dtype, a.fuse, a.size, a.budget_s, a.top, a.ncu,
+               resume_from=a.out if a.resume else None)
     json.dump(res, open(a.out, "w"), indent=1)
     for w in res["winners"]:
         print("WINNER %s  %.4f ms  %.0f GB/s (%.1f%% of %.0f)  drstencil%s" %
