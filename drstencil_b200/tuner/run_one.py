@@ -2,6 +2,7 @@
 wraps (stand-in for the reference's compiled bin/<cfg>, compile_run.sh:5).
 
     python -m drstencil_b200.tuner.run_one <stc> [--3d] [--size L M N] [--launches n] -- <drstencil options>
+    python -m drstencil_b200.tuner.run_one --preset c2 [--launches n]
 """
 import argparse
 import sys
@@ -31,7 +32,8 @@ def knobs_from_argv(argv):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("stc")
+    ap.add_argument("stc", nargs="?")
+    ap.add_argument("--preset", help="a name from drstencil_b200/presets.py instead of <stc> + options")
     ap.add_argument("--3d", dest="is3d", action="store_true")
     ap.add_argument("--size", type=int, nargs="+")
     ap.add_argument("--launches", type=int, default=6)
@@ -41,7 +43,11 @@ def main():
         cut = argv.index("--")
         argv, rest = argv[:cut], argv[cut + 1:]
     a = ap.parse_args(argv)
-    kn = knobs_from_argv(rest)
+    if a.preset:
+        from ..presets import PRESETS
+        a.stc, kn = PRESETS[a.preset]
+    else:
+        kn = knobs_from_argv(rest)
     st = Stencil.from_file(a.stc, a.is3d or None)
     if a.size:
         st.set_size(a.size)
