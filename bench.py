@@ -43,6 +43,8 @@ WORKLOADS = {
     "c5": ("c5", 100, "3d7pt_star fp64 1536^3 slab-decomposed along k, 100 timesteps"),
     "c4t2": ("c4t2", 16, "EXTRA (not in BASELINE.json): 3d7pt_star fp64 768^3 with in-kernel temporal depth 2, 16 timesteps"),
     "c5t2": ("c5t2", 20, "EXTRA: c5 (3d7pt_star fp64 1536^3) with in-kernel temporal depth 2, 20 timesteps"),
+    "c1t2": ("c1t2", 20, "EXTRA: c1 (2d5pt_star fp64 4096^2) with in-kernel temporal depth 2, 20 timesteps"),
+    "c3t2": ("c3t2", 8, "EXTRA: c3 (2d25pt_box fp32 16384^2) with in-kernel temporal depth 2, 8 timesteps"),
 }
 
 
@@ -295,7 +297,7 @@ def per_config(args):
     from drstencil_b200.presets import PRESETS
     peak, _ = measured_peak()
     out = []
-    for wl in ("c1", "c2", "c3", "c4", "c4t2", "c5t2"):
+    for wl in ("c1", "c2", "c3", "c4", "c1t2", "c3t2", "c4t2", "c5t2"):
         preset, timesteps, desc = WORKLOADS[wl]
         path, kn = PRESETS[preset]
         st = drs.Stencil.from_file(path)

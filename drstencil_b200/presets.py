@@ -33,4 +33,6 @@ PRESETS = {
     # extra (not a BASELINE.json config): c4 with in-kernel temporal depth 2
     "c4t2": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(step=2)),
     "c5t2": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(step=2)),
+    "c1t2": (_p("baseline", "c1_2d5pt_star.stc"), Knobs(step=2)),
+    "c3t2": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32", step=2, sn=256)),
 }
