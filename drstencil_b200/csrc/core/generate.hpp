@@ -140,7 +140,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         temporal = false;
         int emax = 0;
         for (const auto& [p, c] : st.base) emax = std::max(emax, std::abs(std::get<2>(p)));
-        const bool fits = 32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) >= vec && k.step <= 4 && emax <= vec;
+        const bool fits = 32 * vec - 2 * (((k.step - 1) * emax + vec - 1) / vec * vec) >= vec && k.step <= 4;
         if (fits && !(k.reserved[6] & 2)) fused3d = true;
         else {
             multi3d = true;
@@ -366,10 +366,6 @@ inline void emit_scatter(std::ostringstream& o, const KernelSpec& s) {
 // 3D scatter (drs_sweep3d_t.cuh): P(dk) is the partial sum of the output plane that sees the source
 // plane at k-offset dk; U(dj, di) is the source plane at row/column offsets.
 inline void emit_scatter3(std::ostringstream& o, const KernelSpec& s) {
-    int xh = -1;    // largest |dj| among terms with di != 0 (-1: the operator has no x neighbours)
-    for (const Term& t : s.chain)
-        if (t.di != 0) xh = std::max(xh, std::abs(t.dj));
-    o << "#define DRS_XH_DJ " << xh << "\n";
     o << "#define DRS_SCATTER3(P, U)";
     for (int dk = -s.rk; dk <= s.rk; ++dk) {
         const std::string P = "P(" + std::to_string(dk) + ")";

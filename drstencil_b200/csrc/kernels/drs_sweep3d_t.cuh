@@ -26,7 +26,7 @@
 // width n*r is never written.
 //
 // Generated translation unit must define: DRS_T DRS_NAME DRS_RK DRS_RJ DRS_E DRS_TS DRS_NW DRS_RY
-// DRS_ST DRS_MINB DRS_XH_DJ DRS_SCATTER3(P,U).
+// DRS_ST DRS_MINB DRS_SCATTER3(P,U).
 #pragma once
 #include "drs_common.cuh"
 
@@ -48,9 +48,6 @@ constexpr int DEPTH = 2 * TS * RK + TS - 1;
 static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
 static_assert(TS >= 2, "single-step sweeps use drs_sweep3d.cuh");
 static_assert(WU > 0 && TYU > 0, "tile too small for this depth");
-static_assert(E <= kVec, "x neighbours come from the adjacent lane");
-// rows (|dj| <= XH) of the source plane whose x neighbours are used at all: 0 for star stencils
-constexpr int XH = DRS_XH_DJ;
 
 __device__ __forceinline__ constexpr int mod_k2(int v) { return ((v % K2) + K2) % K2; }
 
@@ -94,37 +91,12 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
             src = reinterpret_cast<const real*>(c.lv + ((s >= 2 ? s - 2 : 0) * 2 + ((n + 1) & 1)) * PLANE_STRIDE);
         }
         const real* mine = src + (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;   // tile row 0, element 0
-        // One 128-bit shared load per row for the thread's own columns; x neighbours come from the
-        // adjacent lanes by shuffle (half the shared-memory wavefronts of scalar neighbour loads --
-        // this kernel is shared-memory bound).  Only level 1 needs true values at the warp's outer
-        // columns (levels >= 2 are invalid there by construction): lanes 0 and 31 fetch them.
-        real u[RY + 2 * RJ][kVec + 2 * E];
-#pragma unroll
-        for (int r = 0; r < RY + 2 * RJ; ++r) {
-            real own[kVec];
-            lds_vec(own, mine + (r - RJ) * WB);
-#pragma unroll
-            for (int v = 0; v < kVec; ++v) u[r][E + v] = own[v];
-            if (E > 0 && r - RJ >= -XH && r - RJ < RY + XH) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    real l = __shfl_up_sync(0xffffffffu, own[kVec - E + e], 1);
-                    real rr = __shfl_down_sync(0xffffffffu, own[e], 1);
-                    if (s == 1) {
-                        if (c.lane == 0) l = mine[(r - RJ) * WB - E + e];
-                        if (c.lane == 31) rr = mine[(r - RJ) * WB + kVec + e];
-                    }
-                    u[r][e] = l;
-                    u[r][E + kVec + e] = rr;
-                }
-            }
-        }
         // ---- scatter into the partial sums of level s ----
 #pragma unroll
         for (int y = 0; y < RY; ++y) {
 #pragma unroll
             for (int v = 0; v < kVec; ++v) {
-#define DRS_U_(dj, di) u[RJ + y + (dj)][E + v + (di)]
+#define DRS_U_(dj, di) mine[(y + (dj)) * WB + v + (di)]
 #define DRS_P_(dk) pw[s - 1][mod_k2(PH - (dk))][y][v]
                 DRS_SCATTER3(DRS_P_, DRS_U_)
 #undef DRS_U_

@@ -54,10 +54,10 @@ def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     out = []
     variants = {
-        "c4": [dict(step=2), dict(step=2, sn=64), dict(step=2, sn=256), dict(step=2, warps=4, min_blocks=4), dict(step=2, warps=16, rows_3d=2, min_blocks=2),
-               dict(step=2, warps=8, rows_3d=2, min_blocks=4), dict(step=2, stages=4), dict(step=2, min_blocks=1),
-               dict(step=3), dict(step=3, warps=8, rows_3d=4, min_blocks=2), dict(step=3, warps=8, rows_3d=4, min_blocks=1), dict(step=4, warps=16, rows_3d=2)],
-        "c5": [dict(step=2)],
+        "c1": [dict(sn=128, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=2, stages=2), dict(sn=56, warps=2, vectors=2, stages=2),
+               dict(sn=112, warps=2, vectors=2, stages=2), dict(sn=111, warps=1, vectors=2, stages=2), dict(sn=111, warps=4, vectors=2, stages=2),
+               dict(sn=110, warps=2, vectors=2, stages=2), dict(sn=148, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=1, stages=2),
+               dict(sn=222, warps=1, vectors=2, stages=2), dict(sn=222, warps=2, vectors=1, stages=2)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
