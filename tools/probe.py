@@ -17,7 +17,7 @@ from drstencil_b200.presets import PRESETS
 PEAK = 6553.6
 
 
-def time_plan(plan, shape, dtype, sweeps=10, warm=3):
+def time_plan(plan, shape, dtype, sweeps=int(os.environ.get('PROBE_SWEEPS', '10')), warm=3):
     A = torch.rand(shape, dtype=dtype, device="cuda")
     B = torch.zeros_like(A)
     bufs = [A, B]
@@ -54,10 +54,12 @@ def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4"]
     out = []
     variants = {
-        "c1": [dict(sn=128, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=2, stages=2), dict(sn=56, warps=2, vectors=2, stages=2),
-               dict(sn=112, warps=2, vectors=2, stages=2), dict(sn=111, warps=1, vectors=2, stages=2), dict(sn=111, warps=4, vectors=2, stages=2),
-               dict(sn=110, warps=2, vectors=2, stages=2), dict(sn=148, warps=2, vectors=2, stages=2), dict(sn=111, warps=2, vectors=1, stages=2),
-               dict(sn=222, warps=1, vectors=2, stages=2), dict(sn=222, warps=2, vectors=1, stages=2)],
+        "c1": [dict(sn=128, warps=2, vectors=2, stages=2, rows_per_stage=4)],
+        "c2": [dict(step=4, sn=256, vectors=2, stages=2)],
+        "c3": [dict(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)],
+        "c4": [dict(sn=16, rows_3d=4), dict(step=2), dict(step=2, stages=4)],
+        "c5": [dict(sn=16, rows_3d=6), dict(sn=16, rows_3d=4), dict(sn=16, rows_3d=8), dict(sn=32, rows_3d=6), dict(sn=32, rows_3d=8),
+               dict(sn=64, rows_3d=8), dict(sn=24, rows_3d=6), dict(sn=16, rows_3d=6, warps=4), dict(sn=16, rows_3d=6, warps=1)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
