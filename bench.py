@@ -406,7 +406,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world > 1 and (args.workload in (None, "c5")):   # world == 1 sweeps the whole grid on one GPU
         from drstencil_b200 import slab
-        line = slab.bench_slab(args, rank, world, WORKLOADS["c5"], measured_peak())
+        sampler = ClockSampler(torch.cuda.current_device())
+        line = slab.bench_slab(args, rank, world, WORKLOADS["c5"], measured_peak(), sampler.start, sampler.stop)
     else:
         line, plan = run_single(args, rank, world)
         del plan                     # frees the device pair drs_run_host allocated

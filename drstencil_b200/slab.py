@@ -264,8 +264,9 @@ class GpuSlab:
         self._peer_ptrs = []
 
 
-def bench_slab(args, rank, world, workload, peak_info):
-    """bench.py's N > 1 leg: c5 (3d7pt_star fp64 1536^3) over `world` GPUs, strong scaling."""
+def bench_slab(args, rank, world, workload, peak_info, timed_start=None, timed_end=None):
+    """bench.py's N > 1 leg: c5 (3d7pt_star fp64 1536^3) over `world` GPUs, strong scaling.
+    `timed_start` / `timed_end` bracket the timed region (clock sampling)."""
     import time
     import torch
     import torch.distributed as dist
@@ -295,11 +296,14 @@ def bench_slab(args, rank, world, workload, peak_info):
     torch.cuda.synchronize()
     l0 = slab.plan.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if timed_start:
+        timed_start()
     e0.record()
     for _ in range(args.steps):
         slab.run(timesteps)
     e1.record()
     slab.plan.sync_check()
+    clocks = timed_end() if timed_end else None
     secs = e0.elapsed_time(e1) * 1e-3
     t = torch.tensor([secs], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +334,7 @@ def bench_slab(args, rank, world, workload, peak_info):
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "peak_source": peak_src, "kernel": info.kernel_name, "per": "GPU (rank 0's slab)",
                      "algorithmic_bytes_per_launch": local_bytes, "launch_ms": secs / sweep_launches * 1e3},
+        "clocks": clocks,
     }
     # e2e: pinned host slab -> device, the schedule, result back (every step)
     own = slab.owned(0)
