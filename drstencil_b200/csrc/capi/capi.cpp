@@ -49,7 +49,6 @@ struct Driver {
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              CUstream, void**, void**) = nullptr;
-    CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
     CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
@@ -83,7 +82,6 @@ Driver& driver() {
         ok &= get("cuFuncSetAttribute", (void**)&d.FuncSetAttribute);
         ok &= get("cuFuncGetAttribute", (void**)&d.FuncGetAttribute);
         ok &= get("cuLaunchKernel", (void**)&d.LaunchKernel);
-        ok &= get("cuLaunchKernelEx", (void**)&d.LaunchKernelEx);
         ok &= get("cuTensorMapEncodeTiled", (void**)&d.TensorMapEncodeTiled);
         ok &= get("cuGetErrorString", (void**)&d.GetErrorString);
         d.ok = ok;
@@ -424,21 +422,8 @@ int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int 
     const long long ctas = (tiles + p->spec.tiles_per_cta() - 1) / p->spec.tiles_per_cta();
     if (ctas > 0x7fffffffLL) return fail(DRS_E_ARG, "grid too large");
     void* args[] = {tm, &q};
-    // programmatic dependent launch: the sweep may become resident (barrier set-up, index arithmetic)
-    // while the previous kernel of the stream drains; it touches no grid data before griddepcontrol.wait
-    static const bool pdl = getenv("DRS_NO_PDL") == nullptr;
-    CUlaunchAttribute attr;
-    attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
-    attr.value.programmaticStreamSerializationAllowed = 1;
-    CUlaunchConfig cfg;
-    std::memset(&cfg, 0, sizeof cfg);
-    cfg.gridDimX = (unsigned)ctas; cfg.gridDimY = 1; cfg.gridDimZ = 1;
-    cfg.blockDimX = (unsigned)(p->spec.nw * 32); cfg.blockDimY = 1; cfg.blockDimZ = 1;
-    cfg.sharedMemBytes = (unsigned)p->spec.smem_bytes();
-    cfg.hStream = (CUstream)stream;
-    cfg.attrs = &attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    CUresult r = driver().LaunchKernelEx(&cfg, p->f_sweep, args, nullptr);
+    CUresult r = driver().LaunchKernel(p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
+                                       (unsigned)p->spec.smem_bytes(), (CUstream)stream, args, nullptr);
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch dr_: " + cu_err(r));
     p->launches++;
     return DRS_OK;

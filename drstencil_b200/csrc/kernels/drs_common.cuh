@@ -96,15 +96,6 @@ __device__ __forceinline__ bool mbar_wait(drs_u64* bar, drs_u32 parity, int* fau
     return false;
 }
 
-// Programmatic dependent launch: a sweep launched with the stream-serialisation attribute may become
-// resident while the previous kernel in the stream is still draining; griddep_launch() lets the
-// next kernel do the same with respect to this one, griddep_wait() blocks until the previous kernel
-// has completed and its writes are visible.  Everything that touches the grids (the first TMA load
-// included) comes after the wait; only barrier set-up and index arithmetic overlap.  Both are no-ops
-// for ordinary launches.
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // TMA tile loads: global -> shared, completion counted in bytes on an mbarrier.
 __device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map, int x, int y, drs_u64* bar) {
     asm volatile(

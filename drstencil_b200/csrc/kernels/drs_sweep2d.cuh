@@ -236,7 +236,6 @@ __device__ __forceinline__ bool phases(real (&w)[NLV][R2][SW], const Stream& st,
 
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    griddep_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const drs_i64 tile = (drs_i64)blockIdx.x * NW + warp;
     if (tile >= (drs_i64)p.nxs * p.nys) return;
@@ -285,7 +284,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.N = p.N;
     t.out = p.out;
 
-    griddep_wait();      // the previous sweep (which wrote our input and read our output) is complete
     if (lane == 0) {
         for (int c = 0; c < ST && c < st.NCH; ++c) st.issue(c);
     }

@@ -155,7 +155,6 @@ __device__ __forceinline__ bool phases(real (&q)[K2][RY][kVec], const Stream& st
 
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    griddep_launch();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const drs_i64 tile = (drs_i64)blockIdx.x * NW + warp;
     const drs_i64 per_chunk = (drs_i64)p.nxs * p.nys;
@@ -215,7 +214,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.lo0 = p.push_lo0; t.lo1 = p.push_lo1; t.lo_shift = p.peer_lo_shift;
     t.hi0 = p.push_hi0; t.hi1 = p.push_hi1; t.hi_shift = p.peer_hi_shift;
 
-    griddep_wait();      // the previous sweep (which wrote our input and read our output) is complete
     if (lane == 0) {
         for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
     }

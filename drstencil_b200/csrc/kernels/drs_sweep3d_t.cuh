@@ -168,7 +168,6 @@ __device__ __forceinline__ bool phases(real (&pw)[TS][K2][RY][kVec], const Ctx& 
 
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    griddep_launch();
     Ctx c;
     c.warp = threadIdx.x >> 5;
     c.lane = threadIdx.x & 31;
@@ -230,7 +229,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.lo0 = p.push_lo0; c.lo1 = p.push_lo1; c.lo_shift = p.peer_lo_shift;
     c.hi0 = p.push_hi0; c.hi1 = p.push_hi1; c.hi_shift = p.peer_hi_shift;
 
-    griddep_wait();      // the previous sweep (which wrote our input and read our output) is complete
     if (threadIdx.x == 0) {
         for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
     }
