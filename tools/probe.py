@@ -58,8 +58,8 @@ def main():
         "c2": [dict(step=4, sn=256, vectors=2, stages=2)],
         "c3": [dict(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)],
         "c4": [dict(sn=16, rows_3d=4), dict(step=2), dict(step=2, stages=4)],
-        "c5": [dict(sn=64, rows_3d=8), dict(sn=128, rows_3d=8), dict(sn=96, rows_3d=8), dict(sn=64, rows_3d=6), dict(sn=128, rows_3d=6),
-               dict(sn=64, rows_3d=8, stages=8), dict(sn=64, rows_3d=8, min_blocks=3), dict(sn=48, rows_3d=8), dict(sn=256, rows_3d=8)],
+        "c5": [dict(step=2), dict(step=2, stages=4), dict(step=2, sn=64), dict(step=2, sn=64, stages=4), dict(step=2, sn=256),
+               dict(step=2, sn=32), dict(step=2, warps=4, min_blocks=4), dict(step=2, warps=4, min_blocks=4, stages=4)],
     }
     for cfg in which:
         path, _ = PRESETS[cfg]
