@@ -93,6 +93,7 @@ def lib():
         "drs_run": (i32, [vp, vp, vp, i32, vp, P(i32)]),
         "drs_gold_run": (i32, [vp, vp, vp, i32, vp, P(i32)]),
         "drs_run_host": (i32, [vp, vp, vp, i32, P(ctypes.c_float)]),
+        "drs_plan_set_host_block": (i32, [vp, ll]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -410,6 +411,10 @@ class Plan:
         ms = ctypes.c_float()
         _check(lib().drs_run_host(self._h, _ptr(h_a), _ptr(h_b) or None, iterations, ctypes.byref(ms)))
         return ms.value
+
+    def set_host_block(self, units: int) -> None:
+        """Block thickness (slow-axis units) of the streamed run_host: 0 = auto, < 0 = plain sequence."""
+        _check(lib().drs_plan_set_host_block(self._h, units))
 
     def check_error(self, d_out, d_ref):
         res = (ctypes.c_double * 2)()

@@ -250,6 +250,9 @@ struct drs_plan {
     double* d_res = nullptr;
     std::map<const void*, CUtensorMap> tmaps;
     void* h_dev[2] = {nullptr, nullptr};  // buffers owned by drs_run_host
+    bool h_dev_b_ring_zero = false;       // h_dev[1]'s frozen ring still holds the zeros it was cleared to
+    long long host_block = 0;             // drs_plan_set_host_block: 0 = auto, < 0 = no streaming
+    cudaStream_t hs_up = nullptr, hs_run = nullptr, hs_dn = nullptr;   // streams of the streamed drs_run_host
     void* scratch[2] = {nullptr, nullptr};  // intermediate time levels of multi-launch 3D temporal sweeps
     long long launches = 0;
     // slab mode
@@ -335,8 +338,11 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     return DRS_OK;
 }
 
-// ring = frozen ring width of this launch (spec.halo, or the sub-step's share of it)
-void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int ring = -1) {
+struct SlowRange { long long lo, hi; };   // output range along the slow axis, local indices
+
+// ring = frozen ring width of this launch (spec.halo, or the sub-step's share of it);
+// sub  = restrict the launch to these slow-axis outputs (time-skewed blocks of drs_run_host)
+void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int ring = -1, const SlowRange* sub = nullptr) {
     const drs::KernelSpec& s = p->spec;
     std::memset(&q, 0, sizeof q);
     q.in = in; q.out = out;
@@ -361,6 +367,7 @@ void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int
             q.peer_hi_shift = org - (p->upper_lo - ghost);
         }
     }
+    if (sub) { q.slow_lo = std::max(q.slow_lo, sub->lo); q.slow_hi = std::min(q.slow_hi, sub->hi); }
     if (q.slow_hi < q.slow_lo) q.slow_hi = q.slow_lo;
     const long long a0 = (q.halo / s.vec()) * s.vec();
     const long long xspan = std::max<long long>(0, (q.N - q.halo) - a0);
@@ -388,7 +395,7 @@ int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     return DRS_OK;
 }
 
-int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring);
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub = nullptr);
 
 int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     if (in == out) return fail(DRS_E_ARG, "d_in and d_out must differ");
@@ -411,12 +418,12 @@ int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     return DRS_OK;
 }
 
-int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring) {
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub) {
     CUtensorMap* tm = nullptr;
     int rc = tensor_map_for(p, in, &tm);
     if (rc != DRS_OK) return rc;
     DevParams q;
-    fill_params(p, in, out, q, ring);
+    fill_params(p, in, out, q, ring, sub);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
     if (tiles <= 0) return DRS_OK;
     const long long ctas = (tiles + p->spec.tiles_per_cta() - 1) / p->spec.tiles_per_cta();
@@ -578,6 +585,7 @@ void drs_plan_destroy(drs_plan* p) {
         cudaFree(p->d_res);
         for (void* b : p->h_dev) if (b) cudaFree(b);
         for (void* b : p->scratch) if (b) cudaFree(b);
+        for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) if (st) cudaStreamDestroy(st);
         if (p->mod) driver().ModuleUnload(p->mod);
     }
     delete p;
@@ -668,6 +676,103 @@ int drs_plan_sync_check(drs_plan* p, void* stream) {
     return DRS_OK;
 }
 
+// Slow-axis units per block of the streamed host run, 0 = run the plain copy-sweep-copy sequence.
+// A block must be at least two halos thick (see run_host_streamed); blocks of >= 32 MiB keep the
+// copy engines efficient, at most ~16 of them keep the number of small launches low.
+static long long host_block_units(const drs_plan* p, int sweeps) {
+    const drs::KernelSpec& s = p->spec;
+    if (p->host_block < 0 || p->slab || !s.tma_ok || s.sub_launches > 1 || sweeps <= 0) return 0;
+    const long long slow = p->local_slow(), H = s.halo;
+    const double unit = (double)(s.dim == 3 ? p->st.M * p->st.N : p->st.N) * s.esize();
+    long long S = p->host_block;
+    if (S == 0) {
+        const double target = std::max(32.0 * 1048576.0, unit * (double)slow / 16.0);
+        S = (long long)std::ceil(target / unit);
+        S = (S + s.chunk - 1) / s.chunk * s.chunk;     // whole tiles per launch
+    }
+    S = std::max<long long>(S, std::max<long long>(2 * H, 1));
+    return S < slow ? S : 0;
+}
+
+// The emitted main()'s data path (H2D, the ping-pong schedule, D2H) with the three phases
+// overlapped by TIME SKEWING along the slow axis.  The grid is cut into blocks of S planes (rows
+// in 2D); block b runs ALL n sweeps before block b+1 starts, its output range sliding down by one
+// halo per sweep: sweep s of block b produces [b*S - s*H, (b+1)*S - s*H), clamped to the interior.
+// With S >= 2*H this order honours every dependency of the plain schedule in place, on the same
+// two buffers:
+//   * what sweep s reads, [b*S - s*H - H, (b+1)*S - s*H + H) of level s-1, was produced by blocks
+//     b-1 and b at sweep s-1, and block b-1's later sweeps (s+1, s+3, ...) write strictly below it;
+//   * what it overwrites (level s-2) is no longer needed: block b+1 reads level s-2 from
+//     (b+1)*S - s*H upwards only.
+// A sweep is a pure function of its input array, so the result equals the plain schedule bit for
+// bit.  Block b needs only the first (b+1)*S planes of A on the device and its final planes never
+// change afterwards, so the upload of later blocks and the download of earlier ones run on the two
+// copy engines while the SMs sweep -- the wall time tends to max(H2D, sweeps, D2H) instead of their sum.
+static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t bytes, float* device_ms) {
+    const drs::KernelSpec& spec = p->spec;
+    const long long slow = p->local_slow(), H = spec.halo;
+    const size_t unit = bytes / (size_t)slow;
+    const int B = (int)((slow + S - 1) / S);
+    for (cudaStream_t* st : {&p->hs_up, &p->hs_run, &p->hs_dn})
+        if (!*st && cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(DRS_E_CUDA, "cudaStreamCreate failed");
+    char* dA = (char*)p->h_dev[0];
+    char* dB = (char*)p->h_dev[1];
+    char* hA = (char*)h_a;
+    auto cut = [&](int b, int s) -> long long {   // first output plane of block b at sweep s (1-based)
+        if (b <= 0) return H;
+        if (b >= B) return slow - H;
+        return std::min(std::max((long long)b * S - (long long)s * H, H), slow - H);
+    };
+    std::vector<cudaEvent_t> up(B), done(B);
+    cudaEvent_t e0, e1, fin;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventCreateWithFlags(&fin, cudaEventDisableTiming);
+    for (int b = 0; b < B; ++b) {
+        cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    cudaEventRecord(e0, 0);
+    for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamWaitEvent(st, e0, 0);
+    for (int b = 0; b < B; ++b) {
+        const long long lo = (long long)b * S, hi = std::min(slow, lo + S);
+        cudaMemcpyAsync(dA + lo * unit, hA + lo * unit, (size_t)(hi - lo) * unit, cudaMemcpyHostToDevice, p->hs_up);
+        cudaEventRecord(up[b], p->hs_up);
+    }
+    // the reference's h_out is all zeros (getZero2DArray); only its frozen ring is ever read before
+    // it is written, and no sweep writes the ring, so one clear serves every later call
+    if (!p->h_dev_b_ring_zero) cudaMemsetAsync(dB, 0, bytes, p->hs_run);
+    p->h_dev_b_ring_zero = true;
+    int rc = DRS_OK;
+    for (int b = 0; b < B && rc == DRS_OK; ++b) {
+        cudaStreamWaitEvent(p->hs_run, up[b], 0);
+        for (int s = 1; s <= n && rc == DRS_OK; ++s) {
+            const SlowRange r = {cut(b, s), cut(b + 1, s)};
+            if (r.hi <= r.lo) continue;
+            rc = (s & 1) ? launch_one(p, dA, dB, p->hs_run, -1, &r) : launch_one(p, dB, dA, p->hs_run, -1, &r);
+        }
+        cudaEventRecord(done[b], p->hs_run);
+        cudaStreamWaitEvent(p->hs_dn, done[b], 0);
+        const long long lo = b == 0 ? 0 : cut(b, n), hi = b == B - 1 ? slow : cut(b + 1, n);
+        if (hi > lo)
+            cudaMemcpyAsync(hA + lo * unit, dA + lo * unit, (size_t)(hi - lo) * unit, cudaMemcpyDeviceToHost, p->hs_dn);
+    }
+    cudaEventRecord(fin, p->hs_dn);
+    cudaStreamWaitEvent(0, fin, 0);
+    cudaEventRecord(e1, 0);
+    int rc2 = drs_plan_sync_check(p, nullptr);
+    for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(fin);
+    for (int b = 0; b < B; ++b) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); }
+    if (device_ms) *device_ms = ms;
+    const cudaError_t ce = cudaGetLastError();
+    if (rc == DRS_OK && rc2 == DRS_OK && ce != cudaSuccess)
+        return fail(DRS_E_CUDA, std::string("streamed host run: ") + cudaGetErrorString(ce));
+    return rc != DRS_OK ? rc : rc2;
+}
+
 int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* device_ms) {
     if (!p || !h_a) return fail(DRS_E_ARG, "null argument");
     int rc = ensure_loaded(p);
@@ -676,12 +781,17 @@ int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* devic
     for (int i = 0; i < 2; ++i)
         if (!p->h_dev[i] && cudaMalloc(&p->h_dev[i], bytes) != cudaSuccess)
             return fail(DRS_E_CUDA, "cudaMalloc of the sweep buffers failed");
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    const long long S = h_b ? 0 : host_block_units(p, n);
+    if (S > 0) return run_host_streamed(p, h_a, n, S, bytes, device_ms);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, 0);
     cudaMemcpyAsync(p->h_dev[0], h_a, bytes, cudaMemcpyHostToDevice, 0);
     if (h_b) cudaMemcpyAsync(p->h_dev[1], h_b, bytes, cudaMemcpyHostToDevice, 0);
     else cudaMemsetAsync(p->h_dev[1], 0, bytes, 0);   // the reference's h_out is all zeros (getZero2DArray)
+    p->h_dev_b_ring_zero = h_b == nullptr;
     rc = run_schedule(p, p->h_dev[0], p->h_dev[1], iterations, nullptr, nullptr, false);
     cudaMemcpyAsync(h_a, p->h_dev[0], bytes, cudaMemcpyDeviceToHost, 0);
     cudaEventRecord(e1, 0);
@@ -691,6 +801,12 @@ int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* devic
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (device_ms) *device_ms = ms;
     return rc != DRS_OK ? rc : rc2;
+}
+
+int drs_plan_set_host_block(drs_plan* p, long long units) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    p->host_block = units;
+    return DRS_OK;
 }
 
 int drs_check_error(drs_plan* p, const void* d_out, const void* d_ref, double res[2]) {

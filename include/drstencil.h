@@ -140,8 +140,16 @@ int drs_gold_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream
 /* the whole emitted main() data path on HOST buffers (codegen_2d.hpp:572-583,604-619,647):
  * H2D of a and b, the schedule, D2H of a.  h_a/h_b hold L*M*N elements of the plan's dtype;
  * h_b == NULL stands for the all-zero second buffer the reference always uses (common.hpp:34-45)
- * and is cleared on the device instead of being copied. */
+ * and is cleared on the device instead of being copied.
+ * With h_b == NULL the three phases are overlapped by time skewing along the slow axis: the grid
+ * is cut into blocks of planes (rows in 2D), each block runs the whole schedule with its output
+ * range sliding down one Halo per sweep while later blocks upload and earlier ones download
+ * (pinned host memory needed for the overlap; results are bit-identical to the plain sequence).
+ * *device_ms = device time from the first copy to the last, CUDA events. */
 int drs_run_host(drs_plan *p, void *h_a, void *h_b, int iterations, float *device_ms);
+/* block thickness of the streamed drs_run_host in slow-axis units: 0 = chosen by the engine
+ * (>= 32 MiB, about 16 blocks), < 0 = plain copy-sweep-copy, > 0 = as given (raised to 2*Halo) */
+int drs_plan_set_host_block(drs_plan *p, long long units);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
 int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);
