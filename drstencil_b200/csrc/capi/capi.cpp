@@ -697,7 +697,8 @@ static long long host_block_units(const drs_plan* p, int sweeps) {
 // The emitted main()'s data path (H2D, the ping-pong schedule, D2H) with the three phases
 // overlapped by TIME SKEWING along the slow axis.  The grid is cut into blocks of S planes (rows
 // in 2D); block b runs ALL n sweeps before block b+1 starts, its output range sliding down by one
-// halo per sweep: sweep s of block b produces [b*S - s*H, (b+1)*S - s*H), clamped to the interior.
+// halo per sweep: sweep s of block b produces [b*S - s*H, (b+1)*S - s*H), clamped to the interior
+// (written for equal blocks; the edges may be any increasing sequence with gaps >= 2*H).
 // With S >= 2*H this order honours every dependency of the plain schedule in place, on the same
 // two buffers:
 //   * what sweep s reads, [b*S - s*H - H, (b+1)*S - s*H + H) of level s-1, was produced by blocks
@@ -712,7 +713,21 @@ static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t 
     const drs::KernelSpec& spec = p->spec;
     const long long slow = p->local_slow(), H = spec.halo;
     const size_t unit = bytes / (size_t)slow;
-    const int B = (int)((slow + S - 1) / S);
+    // block edges: the first and the last block are thin (a quarter of S, at least 2*H) -- the
+    // first one's upload and the last one's download (S_last + n*H planes) are the only copies that
+    // nothing overlaps
+    std::vector<long long> edge;
+    {
+        const long long thin = std::max<long long>(2 * H, std::max<long long>(S / 4, 1));
+        edge.push_back(0);
+        long long at = std::min(thin, slow);
+        while (at < slow) {
+            edge.push_back(at);
+            at += (slow - at - thin > S) ? S : ((slow - at > 2 * thin) ? slow - at - thin : slow - at);
+        }
+        edge.push_back(slow);
+    }
+    const int B = (int)edge.size() - 1;
     for (cudaStream_t* st : {&p->hs_up, &p->hs_run, &p->hs_dn})
         if (!*st && cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess)
             return fail(DRS_E_CUDA, "cudaStreamCreate failed");
@@ -722,7 +737,7 @@ static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t 
     auto cut = [&](int b, int s) -> long long {   // first output plane of block b at sweep s (1-based)
         if (b <= 0) return H;
         if (b >= B) return slow - H;
-        return std::min(std::max((long long)b * S - (long long)s * H, H), slow - H);
+        return std::min(std::max(edge[b] - (long long)s * H, H), slow - H);
     };
     std::vector<cudaEvent_t> up(B), done(B);
     cudaEvent_t e0, e1, fin;
@@ -735,7 +750,7 @@ static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t 
     cudaEventRecord(e0, 0);
     for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamWaitEvent(st, e0, 0);
     for (int b = 0; b < B; ++b) {
-        const long long lo = (long long)b * S, hi = std::min(slow, lo + S);
+        const long long lo = edge[b], hi = edge[b + 1];
         cudaMemcpyAsync(dA + lo * unit, hA + lo * unit, (size_t)(hi - lo) * unit, cudaMemcpyHostToDevice, p->hs_up);
         cudaEventRecord(up[b], p->hs_up);
     }
