@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -419,6 +420,17 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_RK " << s.rk << "\n#define DRS_RJ " << s.rj << "\n#define DRS_E " << s.e << "\n";
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
+    // development aid: DRS_EXTRA_DEFINES="A=1;B=2" adds `#define A 1` ... to the translation unit
+    // (tools/probe_shape.py experiments; part of the source, hence of the cubin cache key)
+    if (const char* xd = std::getenv("DRS_EXTRA_DEFINES")) {
+        std::string all = xd, item;
+        std::istringstream is(all);
+        while (std::getline(is, item, ';')) {
+            if (item.empty()) continue;
+            const size_t eq = item.find('=');
+            o << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
+        }
+    }
     emit_chain(o, "DRS_CHAIN", s.chain);
     if (s.ts > 1 && s.dim == 2) emit_scatter(o, s);
     if (s.fused3d) emit_scatter3(o, s);

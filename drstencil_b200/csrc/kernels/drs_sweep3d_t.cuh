@@ -12,10 +12,12 @@
 //   * the sub-steps are evaluated in SCATTER form, as in the 2D temporal kernel: a plane of time
 //     level s-1 is pushed into the partial sums of the 2*RK+1 level-s planes it touches; per-thread
 //     state is `pw[TS][2*RK+1][RY][V]`, rotated statically;
-//   * a completed plane of an intermediate level is published to a shared-memory plane buffer
-//     (double-buffered by iteration parity) from which every warp -- the owner included -- reads it
-//     back with its x/y neighbours in the next iteration; one __syncthreads per plane orders
-//     publication, consumption and the hand-back of the TMA stage;
+//   * a completed plane of an intermediate level stays in the registers of the thread that
+//     produced it (the partial-sum slot is not re-initialised before the next level has consumed
+//     it); its column halo travels by warp shuffle, and only the rows at the top and bottom of
+//     each warp's band are published to a shared-memory plane buffer (double-buffered by
+//     iteration parity) for the warp above/below; one __syncthreads per plane orders publication,
+//     consumption and the hand-back of the TMA stage;
 //   * levels are evaluated top-down inside an iteration, so their chains are independent and the
 //     wait for the newest input plane comes last;
 //   * the tile loses RJ rows / E columns per level at its edges (overlapped tiling): a CTA of
@@ -29,6 +31,18 @@
 // DRS_ST DRS_MINB DRS_SCATTER3(P,U).
 #pragma once
 #include "drs_common.cuh"
+
+// How much of a source plane a thread takes from registers / its neighbour lanes instead of shared
+// memory (the kernel is shared-memory-bandwidth bound; B200, c4 depth 2: 589 / 646 / 657 / 667 / 687
+// GStencil/s for 0..4).  Kept as a switch for ablation (DRS_EXTRA_DEFINES="DRS_T3_OWNREG=n").
+//   0  every operand is read back from shared memory
+//   1  levels >= 2: own rows/columns from the partial-sum registers that still hold them
+//   2  + their column halo by warp shuffle
+//   3  + only the edge rows of a completed plane are published (nobody else reads the rest)
+//   4  + level 1: own vectors loaded once (128-bit), column halo shuffled as well
+#ifndef DRS_T3_OWNREG
+#define DRS_T3_OWNREG 4
+#endif
 
 namespace drs {
 namespace s3t {
@@ -50,6 +64,7 @@ static_assert(TS >= 2, "single-step sweeps use drs_sweep3d.cuh");
 static_assert(WU > 0 && TYU > 0, "tile too small for this depth");
 
 __device__ __forceinline__ constexpr int mod_k2(int v) { return ((v % K2) + K2) % K2; }
+__device__ __forceinline__ constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 struct Ctx {
     unsigned char* ring;     // ST input planes
@@ -92,23 +107,88 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         }
         const real* mine = src + (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;   // tile row 0, element 0
         // ---- scatter into the partial sums of level s ----
+#if DRS_T3_OWNREG
+        // Levels >= 2: the thread's own part of the source plane is still in its registers -- the slot
+        // of level s-1 completed by the previous iteration is only re-initialised by level s-1's scatter,
+        // which runs after this one (levels go top-down).  Only the halo (rows above/below the thread's
+        // rows, columns left/right of its vector) is read back from the published plane.
+#if DRS_T3_OWNREG >= 2
+        // ... and the column halo comes from the adjacent lanes by shuffle (lanes 0 / 31 get their own
+        // value: those columns are lost at this level anyway)
+        real xl[RY][E > 0 ? E : 1], xr[RY][E > 0 ? E : 1];
+        if (s >= 2) {
+#pragma unroll
+            for (int y = 0; y < RY; ++y)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    xl[y][e] = __shfl_up_sync(0xffffffffu, pw[s >= 2 ? s - 2 : 0][mod_k2(PH - 1 - RK)][y][kVec - E + e], 1);
+                    xr[y][e] = __shfl_down_sync(0xffffffffu, pw[s >= 2 ? s - 2 : 0][mod_k2(PH - 1 - RK)][y][e], 1);
+                }
+        }
+#if DRS_T3_OWNREG >= 4
+        // level 1: the input plane's own vectors are loaded once (128-bit) and its column halo is
+        // shuffled as well; the edge lanes take theirs from the staged box when the lost columns do
+        // not already cover them
+        real u0[RY][kVec];
+        if (s == 1) {
+#pragma unroll
+            for (int y = 0; y < RY; ++y) lds_vec(u0[y], mine + y * WB);
+#pragma unroll
+            for (int y = 0; y < RY; ++y)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    xl[y][e] = __shfl_up_sync(0xffffffffu, u0[y][kVec - E + e], 1);
+                    xr[y][e] = __shfl_down_sync(0xffffffffu, u0[y][e], 1);
+                    if constexpr (HW < TS * E) {
+                        if (c.lane == 0) xl[y][e] = mine[y * WB - E + e];
+                        if (c.lane == 31) xr[y][e] = mine[y * WB + kVec + e];
+                    }
+                }
+        }
+#endif
+#define DRS_XNBR_(yy, xx) ((xx) < 0 ? xl[yy][E + (xx)] : xr[yy][(xx) - kVec])
+#else
+#define DRS_XNBR_(yy, xx) mine[(yy) * WB + (xx)]
+#endif
+#define DRS_OWN_(yy, xx) (((xx) >= 0 && (xx) < kVec) ? pw[s >= 2 ? s - 2 : 0][mod_k2(PH - 1 - RK)][clampi(yy, 0, RY - 1)][clampi(xx, 0, kVec - 1)] \
+                                                     : DRS_XNBR_(clampi(yy, 0, RY - 1), xx))
+#if DRS_T3_OWNREG >= 4
+#define DRS_OWN0_(yy, xx) (((xx) >= 0 && (xx) < kVec) ? u0[clampi(yy, 0, RY - 1)][clampi(xx, 0, kVec - 1)] \
+                                                      : DRS_XNBR_(clampi(yy, 0, RY - 1), xx))
+#define DRS_U_(dj, di) (((y + (dj)) >= 0 && (y + (dj)) < RY) ? (s >= 2 ? DRS_OWN_(y + (dj), v + (di)) : DRS_OWN0_(y + (dj), v + (di))) \
+                                                             : mine[(y + (dj)) * WB + v + (di)])
+#else
+#define DRS_U_(dj, di) ((s >= 2 && (y + (dj)) >= 0 && (y + (dj)) < RY) ? DRS_OWN_(y + (dj), v + (di)) : mine[(y + (dj)) * WB + v + (di)])
+#endif
+#else
+#define DRS_U_(dj, di) mine[(y + (dj)) * WB + v + (di)]
+#endif
 #pragma unroll
         for (int y = 0; y < RY; ++y) {
 #pragma unroll
             for (int v = 0; v < kVec; ++v) {
-#define DRS_U_(dj, di) mine[(y + (dj)) * WB + v + (di)]
 #define DRS_P_(dk) pw[s - 1][mod_k2(PH - (dk))][y][v]
                 DRS_SCATTER3(DRS_P_, DRS_U_)
-#undef DRS_U_
 #undef DRS_P_
             }
         }
+#undef DRS_U_
+#if DRS_T3_OWNREG
+#undef DRS_OWN_
+#undef DRS_XNBR_
+#endif
+#if DRS_T3_OWNREG >= 4
+#undef DRS_OWN0_
+#endif
         // ---- the plane of level s completed by this iteration ----
         if (s < TS) {
             real* dst = reinterpret_cast<real*>(c.lv + ((s - 1) * 2 + (n & 1)) * PLANE_STRIDE) +
                         (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;
 #pragma unroll
             for (int y = 0; y < RY; ++y) {
+#if DRS_T3_OWNREG >= 3
+                if (y >= RJ && y < RY - RJ) continue;   // only other warps read the plane back: edge rows suffice
+#endif
                 real o[kVec];
 #pragma unroll
                 for (int v = 0; v < kVec; ++v) o[v] = pw[s < TS ? s - 1 : 0][mod_k2(PH - RK)][y][v];

@@ -120,6 +120,27 @@ def test_fp32_temporal_within_1e5(built):
     assert max_rel(A.cpu().numpy()[inner], ref64[inner]) <= 1e-5
 
 
+@pytest.mark.parametrize("name,step", [("3d7pt_star", 2), ("3d9pt_cross", 2), ("3d7pt_star", 3)])
+def test_fp32_3d_temporal_within_1e5(built, name, step):
+    """The fused 3D temporal kernel in fp32 (four columns per lane, shuffled column halo)."""
+    from oracle import oracle
+    shape = (30, 70, 264)
+    plan = _plan(name, shape, dtype="f32", step=step)
+    assert "drs_sweep3d_t.cuh" in plan.source
+    a64 = oracle.rand_array(shape)
+    A, B = _dev(a64.astype(np.float32)), _dev(np.zeros(shape, np.float32))
+    plan.run(A, B, iterations=2 * step)
+    plan.sync_check()
+    ref64, _ = oracle_run(name, step, shape, 2, np.float64, a0=a64)
+    H = plan.halo
+    inner = tuple(slice(H, -H) for _ in shape)
+    got = A.cpu().numpy()
+    assert max_rel(got[inner], ref64[inner]) <= 1e-5
+    ring = np.ones(shape, bool)
+    ring[inner] = False
+    assert np.array_equal(got[ring], a64.astype(np.float32)[ring])
+
+
 @pytest.mark.parametrize("name,kn", [
     ("2d5pt_star", dict(sn=7)), ("2d5pt_star", dict(sn=1000, stages=2, rows_per_stage=1)),
     ("2d9pt_box", dict(step=3, sn=16, warps=4, stages=8, rows_per_stage=8)),
