@@ -94,6 +94,7 @@ def lib():
         "drs_gold_run": (i32, [vp, vp, vp, i32, vp, P(i32)]),
         "drs_run_host": (i32, [vp, vp, vp, i32, P(ctypes.c_float)]),
         "drs_plan_set_host_block": (i32, [vp, ll]),
+        "drs_plan_set_graph": (i32, [vp, i32]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -411,6 +412,10 @@ class Plan:
         ms = ctypes.c_float()
         _check(lib().drs_run_host(self._h, _ptr(h_a), _ptr(h_b) or None, iterations, ctypes.byref(ms)))
         return ms.value
+
+    def set_graph(self, enable: bool) -> None:
+        """run() as one CUDA graph per (A, B, sweep count) (default) or as plain launches."""
+        _check(lib().drs_plan_set_graph(self._h, int(bool(enable))))
 
     def set_host_block(self, units: int) -> None:
         """Block thickness (slow-axis units) of the streamed run_host: 0 = auto, < 0 = plain sequence."""

@@ -135,6 +135,10 @@ int drs_gold_sweep(drs_plan *p, const void *d_in, void *d_out, void *stream);
 /* the emitted host loop (codegen_2d.hpp:610-613): for (t = 0; t < iterations; t += 2*step)
  * { sweep(A,B); sweep(B,A); } -- result is in A.  Writes the number of sweeps to *sweeps. */
 int drs_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int *sweeps);
+/* drs_run replays its launches as one CUDA graph per (d_a, d_b, sweep count) -- same kernels, same
+ * order, without the gap between dependent launches (matters for grids as small as 4096^2).  On
+ * by default; a stream that is itself being captured always gets plain launches.  0 switches it off. */
+int drs_plan_set_graph(drs_plan *p, int enable);
 /* same schedule with the gold kernel (codegen_2d.hpp:638-642) */
 int drs_gold_run(drs_plan *p, void *d_a, void *d_b, int iterations, void *stream, int *sweeps);
 /* the whole emitted main() data path on HOST buffers (codegen_2d.hpp:572-583,604-619,647):

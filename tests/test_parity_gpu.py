@@ -473,3 +473,42 @@ def test_tuner_smoke(built, tmp_path, monkeypatch):
     res = tune.tune(stc_path("2d9pt_box"), step=2, size=(1024, 1024), budget_s=20.0, top=1, log=lambda *a: None)
     assert res["tried"] >= 3 and res["winners"] and res["winners"][0]["ms_confirmed"] > 0
     assert res["winners"][0]["name"].startswith("fu2d0bx")
+
+
+def test_run_as_cuda_graph_equals_plain_launches(built):
+    """drs_run replays its launches as a CUDA graph by default: same kernels, same count, same
+    bits as plain launches; different sweep counts and buffer pairs get their own graphs; a stream
+    that the caller is capturing gets plain launches (and the caller's graph replays correctly)."""
+    import torch
+    from oracle import oracle
+    shape = (300, 264)
+    plan = _plan("2d5pt_star", shape)
+    a0 = oracle.rand_array(shape)
+    outs = {}
+    for mode in (False, True):
+        plan.set_graph(mode)
+        for iters in (10, 4, 10):
+            A, B = _dev(a0), _dev(np.zeros(shape))
+            l0 = plan.launch_count
+            n = plan.run(A, B, iterations=iters)
+            plan.sync_check()
+            assert n == iters and plan.launch_count - l0 == iters
+            if (iters, False) in outs:
+                assert np.array_equal(A.cpu().numpy(), outs[(iters, False)])
+            outs[(iters, mode)] = A.cpu().numpy()
+    refA, _ = oracle_run("2d5pt_star", 1, shape, 10)
+    assert np.array_equal(outs[(10, True)], refA)
+    # the same plan inside the caller's own graph
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        plan.run(A, B, iterations=2)
+    torch.cuda.current_stream().wait_stream(s)
+    A.copy_(torch.from_numpy(a0)); B.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        plan.run(A, B, iterations=10)
+    g.replay()
+    plan.sync_check()
+    assert np.array_equal(A.cpu().numpy(), refA)
