@@ -95,6 +95,7 @@ def lib():
         "drs_run_host": (i32, [vp, vp, vp, i32, P(ctypes.c_float)]),
         "drs_plan_set_host_block": (i32, [vp, ll]),
         "drs_plan_set_graph": (i32, [vp, i32]),
+        "drs_plan_host_schedule": (i32, [vp, i32, P(ll), i32]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -416,6 +417,15 @@ class Plan:
     def set_graph(self, enable: bool) -> None:
         """run() as one CUDA graph per (A, B, sweep count) (default) or as plain launches."""
         _check(lib().drs_plan_set_graph(self._h, int(bool(enable))))
+
+    def host_schedule(self, iterations: int):
+        """[(kind, block, sweep, lo, hi)] the streamed run_host would execute ([] = plain sequence); no GPU needed."""
+        n = _check(lib().drs_plan_host_schedule(self._h, iterations, None, 0))
+        if n == 0:
+            return []
+        buf = (ctypes.c_longlong * (5 * n))()
+        _check(lib().drs_plan_host_schedule(self._h, iterations, buf, n))
+        return [tuple(buf[5 * i:5 * i + 5]) for i in range(n)]
 
     def set_host_block(self, units: int) -> None:
         """Block thickness (slow-axis units) of the streamed run_host: 0 = auto, < 0 = plain sequence."""

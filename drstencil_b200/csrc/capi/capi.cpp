@@ -24,6 +24,7 @@
 
 #include "../../../include/drstencil.h"
 #include "../core/generate.hpp"
+#include "../core/host_schedule.hpp"
 #include "../core/stencil.hpp"
 #include "emit_program.hpp"
 
@@ -739,7 +740,7 @@ int drs_plan_sync_check(drs_plan* p, void* stream) {
 }
 
 // Slow-axis units per block of the streamed host run, 0 = run the plain copy-sweep-copy sequence.
-// A block must be at least two halos thick (see run_host_streamed); blocks of >= 32 MiB keep the
+// A block must be at least two halos thick (core/host_schedule.hpp); blocks of >= 32 MiB keep the
 // copy engines efficient, at most ~16 of them keep the number of small launches low.
 static long long host_block_units(const drs_plan* p, int sweeps) {
     const drs::KernelSpec& s = p->spec;
@@ -756,51 +757,20 @@ static long long host_block_units(const drs_plan* p, int sweeps) {
     return S < slow ? S : 0;
 }
 
-// The emitted main()'s data path (H2D, the ping-pong schedule, D2H) with the three phases
-// overlapped by TIME SKEWING along the slow axis.  The grid is cut into blocks of S planes (rows
-// in 2D); block b runs ALL n sweeps before block b+1 starts, its output range sliding down by one
-// halo per sweep: sweep s of block b produces [b*S - s*H, (b+1)*S - s*H), clamped to the interior
-// (written for equal blocks; the edges may be any increasing sequence with gaps >= 2*H).
-// With S >= 2*H this order honours every dependency of the plain schedule in place, on the same
-// two buffers:
-//   * what sweep s reads, [b*S - s*H - H, (b+1)*S - s*H + H) of level s-1, was produced by blocks
-//     b-1 and b at sweep s-1, and block b-1's later sweeps (s+1, s+3, ...) write strictly below it;
-//   * what it overwrites (level s-2) is no longer needed: block b+1 reads level s-2 from
-//     (b+1)*S - s*H upwards only.
-// A sweep is a pure function of its input array, so the result equals the plain schedule bit for
-// bit.  Block b needs only the first (b+1)*S planes of A on the device and its final planes never
-// change afterwards, so the upload of later blocks and the download of earlier ones run on the two
-// copy engines while the SMs sweep -- the wall time tends to max(H2D, sweeps, D2H) instead of their sum.
+// The emitted main()'s data path (H2D, the ping-pong schedule, D2H) in the time-skewed block order of
+// core/host_schedule.hpp: uploads on one stream, sweeps on a second, downloads on a third, chained
+// by events -- the wall time tends to max(H2D, sweeps, D2H) instead of their sum.
 static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t bytes, float* device_ms) {
-    const drs::KernelSpec& spec = p->spec;
-    const long long slow = p->local_slow(), H = spec.halo;
+    const long long slow = p->local_slow();
     const size_t unit = bytes / (size_t)slow;
-    // block edges: the first and the last block are thin (a quarter of S, at least 2*H) -- the
-    // first one's upload and the last one's download (S_last + n*H planes) are the only copies that
-    // nothing overlaps
-    std::vector<long long> edge;
-    {
-        const long long thin = std::max<long long>(2 * H, std::max<long long>(S / 4, 1));
-        edge.push_back(0);
-        long long at = std::min(thin, slow);
-        while (at < slow) {
-            edge.push_back(at);
-            at += (slow - at - thin > S) ? S : ((slow - at > 2 * thin) ? slow - at - thin : slow - at);
-        }
-        edge.push_back(slow);
-    }
-    const int B = (int)edge.size() - 1;
+    const drs::HostSchedule hs = drs::plan_host_schedule(slow, p->spec.halo, S, n);
+    const int B = hs.blocks();
     for (cudaStream_t* st : {&p->hs_up, &p->hs_run, &p->hs_dn})
         if (!*st && cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess)
             return fail(DRS_E_CUDA, "cudaStreamCreate failed");
     char* dA = (char*)p->h_dev[0];
     char* dB = (char*)p->h_dev[1];
     char* hA = (char*)h_a;
-    auto cut = [&](int b, int s) -> long long {   // first output plane of block b at sweep s (1-based)
-        if (b <= 0) return H;
-        if (b >= B) return slow - H;
-        return std::min(std::max(edge[b] - (long long)s * H, H), slow - H);
-    };
     std::vector<cudaEvent_t> up(B), done(B);
     cudaEvent_t e0, e1, fin;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -811,28 +781,30 @@ static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t 
     }
     cudaEventRecord(e0, 0);
     for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamWaitEvent(st, e0, 0);
-    for (int b = 0; b < B; ++b) {
-        const long long lo = edge[b], hi = edge[b + 1];
-        cudaMemcpyAsync(dA + lo * unit, hA + lo * unit, (size_t)(hi - lo) * unit, cudaMemcpyHostToDevice, p->hs_up);
-        cudaEventRecord(up[b], p->hs_up);
+    // every upload is queued first: the copy engine runs ahead of the sweeps as far as it can
+    for (const drs::HostStep& st : hs.steps) {
+        if (st.kind != drs::HostStep::UPLOAD) continue;
+        cudaMemcpyAsync(dA + st.lo * unit, hA + st.lo * unit, (size_t)(st.hi - st.lo) * unit, cudaMemcpyHostToDevice, p->hs_up);
+        cudaEventRecord(up[st.block], p->hs_up);
     }
     // the reference's h_out is all zeros (getZero2DArray); only its frozen ring is ever read before
     // it is written, and no sweep writes the ring, so one clear serves every later call
     if (!p->h_dev_b_ring_zero) cudaMemsetAsync(dB, 0, bytes, p->hs_run);
     p->h_dev_b_ring_zero = true;
     int rc = DRS_OK;
-    for (int b = 0; b < B && rc == DRS_OK; ++b) {
-        cudaStreamWaitEvent(p->hs_run, up[b], 0);
-        for (int s = 1; s <= n && rc == DRS_OK; ++s) {
-            const SlowRange r = {cut(b, s), cut(b + 1, s)};
-            if (r.hi <= r.lo) continue;
-            rc = (s & 1) ? launch_one(p, dA, dB, p->hs_run, -1, &r) : launch_one(p, dB, dA, p->hs_run, -1, &r);
+    for (const drs::HostStep& st : hs.steps) {
+        if (rc != DRS_OK) break;
+        if (st.kind == drs::HostStep::UPLOAD) {
+            cudaStreamWaitEvent(p->hs_run, up[st.block], 0);
+        } else if (st.kind == drs::HostStep::SWEEP) {
+            const SlowRange r = {st.lo, st.hi};
+            rc = (st.sweep & 1) ? launch_one(p, dA, dB, p->hs_run, -1, &r) : launch_one(p, dB, dA, p->hs_run, -1, &r);
+        } else {
+            cudaEventRecord(done[st.block], p->hs_run);
+            cudaStreamWaitEvent(p->hs_dn, done[st.block], 0);
+            if (st.hi > st.lo)
+                cudaMemcpyAsync(hA + st.lo * unit, dA + st.lo * unit, (size_t)(st.hi - st.lo) * unit, cudaMemcpyDeviceToHost, p->hs_dn);
         }
-        cudaEventRecord(done[b], p->hs_run);
-        cudaStreamWaitEvent(p->hs_dn, done[b], 0);
-        const long long lo = b == 0 ? 0 : cut(b, n), hi = b == B - 1 ? slow : cut(b + 1, n);
-        if (hi > lo)
-            cudaMemcpyAsync(hA + lo * unit, dA + lo * unit, (size_t)(hi - lo) * unit, cudaMemcpyDeviceToHost, p->hs_dn);
     }
     cudaEventRecord(fin, p->hs_dn);
     cudaStreamWaitEvent(0, fin, 0);
@@ -848,6 +820,24 @@ static int run_host_streamed(drs_plan* p, void* h_a, int n, long long S, size_t 
     if (rc == DRS_OK && rc2 == DRS_OK && ce != cudaSuccess)
         return fail(DRS_E_CUDA, std::string("streamed host run: ") + cudaGetErrorString(ce));
     return rc != DRS_OK ? rc : rc2;
+}
+
+int drs_plan_host_schedule(const drs_plan* p, int iterations, long long* records5, int capacity) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    const long long S = host_block_units(p, n);
+    if (S <= 0) return 0;
+    const drs::HostSchedule hs = drs::plan_host_schedule(p->local_slow(), p->spec.halo, S, n);
+    if (records5) {
+        if (capacity < (int)hs.steps.size()) return fail(DRS_E_ARG, "buffer too small");
+        for (size_t i = 0; i < hs.steps.size(); ++i) {
+            const drs::HostStep& st = hs.steps[i];
+            long long* r = records5 + 5 * i;
+            r[0] = st.kind; r[1] = st.block; r[2] = st.sweep; r[3] = st.lo; r[4] = st.hi;
+        }
+    }
+    return (int)hs.steps.size();
 }
 
 int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* device_ms) {

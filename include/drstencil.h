@@ -154,6 +154,11 @@ int drs_run_host(drs_plan *p, void *h_a, void *h_b, int iterations, float *devic
 /* block thickness of the streamed drs_run_host in slow-axis units: 0 = chosen by the engine
  * (>= 32 MiB, about 16 blocks), < 0 = plain copy-sweep-copy, > 0 = as given (raised to 2*Halo) */
 int drs_plan_set_host_block(drs_plan *p, long long units);
+/* the step list the streamed drs_run_host would execute for `iterations` (needs no GPU): records of five
+ * values {kind (0 upload, 1 sweep, 2 download), block, sweep (1-based; odd: A -> B), lo, hi} with [lo, hi)
+ * the slow-axis range copied / produced; per block: its upload, its sweeps, its download.  Returns the
+ * number of records (pass NULL to query), 0 when the plain sequence would run. */
+int drs_plan_host_schedule(const drs_plan *p, int iterations, long long *records5, int capacity);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
 int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);
