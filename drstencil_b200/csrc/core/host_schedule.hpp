@@ -17,8 +17,8 @@
 // A sweep is a pure function of its input array, so the result equals the plain schedule bit for bit.
 // Block b needs nothing above edge[b+1] on the device, and its final planes never change afterwards:
 // the upload of later blocks and the download of earlier ones can run under the sweeps.
-// tests/test_host_schedule.py replays the step list against the CPU oracle (with not-yet-uploaded
-// planes poisoned) for both extreme interleavings of the copies.
+// tests/test_host_schedule.py replays the step list on the CPU (not-yet-uploaded planes poisoned)
+// for both extreme interleavings of the copies and compares with the plain schedule.
 #pragma once
 #include <algorithm>
 #include <vector>
