@@ -22,6 +22,13 @@
 #pragma once
 #include "drs_common.cuh"
 
+// Ablation switch (DRS_EXTRA_DEFINES="DRS_S3_OWNREG=1"): operands at di != 0 that fall inside the
+// thread's own 128-bit vector come from the register queue instead of the staged plane.  B200:
+// 3d9pt_cross 768^3 338 -> 367 GStencil/s, 3d7pt_star 768^3 unchanged, 1536^3 376 -> 367; off by default.
+#ifndef DRS_S3_OWNREG
+#define DRS_S3_OWNREG 0
+#endif
+
 namespace drs {
 namespace s3d {
 
@@ -104,10 +111,17 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
                 real acc;
                 // operand: own register queue when it is this thread's column inside the tile rows,
                 // else the staged plane (halo rows / neighbouring columns)
+#if DRS_S3_OWNREG
+#define DRS_OPERAND_(dk, dj, di)                                                               \
+    (((v + (di)) >= 0 && (v + (di)) < kVec && (y + (dj)) >= 0 && (y + (dj)) < RY)              \
+         ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][clampi(v + (di), 0, kVec - 1)]         \
+         : sp[(dk) + RK][(y + (dj)) * WB + v + (di)])
+#else
 #define DRS_OPERAND_(dk, dj, di)                                                               \
     (((di) == 0 && (y + (dj)) >= 0 && (y + (dj)) < RY)                                         \
          ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][v]                                     \
          : sp[(dk) + RK][(y + (dj)) * WB + v + (di)])
+#endif
 #define DRS_MUL_(dk, dj, di, c) acc = rmul(DRS_OPERAND_(dk, dj, di), (real)(c));
 #define DRS_FMA_(dk, dj, di, c) acc = rfma(DRS_OPERAND_(dk, dj, di), (real)(c), acc);
                 DRS_CHAIN(DRS_MUL_, DRS_FMA_)
