@@ -133,41 +133,58 @@ def time_steps(plan, A, B, timesteps, steps, warmup):
     return e0.elapsed_time(e1) * 1e-3, plan.launch_count - l0
 
 
+class CpuSample:
+    """The oracle port on all host cores over a bounded sample of a workload: the composed operator
+    of the workload (gold restatement) swept over a sub-grid with the workload's full plane / row
+    size, so that the cache behaviour per plane is the real one; only the slow axis is cut."""
+
+    def __init__(self, workload):
+        import numpy as np
+        from oracle import oracle
+        import drstencil_b200 as drs
+        from drstencil_b200.presets import PRESETS
+        self.oracle = oracle
+        self.workload = workload
+        path, kn = PRESETS[WORKLOADS[workload][0]]
+        is3d = os.path.basename(path)[3:].startswith("3d")
+        s = oracle.parse_stc(path, is3d)
+        self.step = kn.step
+        pts = oracle.compose(s.points, self.step)
+        self.offs, self.coefs = oracle.terms(pts)
+        self.halo, _ = oracle.order_dist(pts, s.dim)
+        dtype = np.float32 if kn.dtype == drs.F32 else np.float64
+        # ~3.5 GiB per array at most: 192 planes of c5, 4096 rows of the 16384-wide 2D grids
+        self.shape = (min(s.L, 192), s.M, s.N) if is3d else (min(s.M, 4096), s.N)
+        self.a = oracle.lcg_array(self.shape, dtype, 1)
+        self.b = oracle.lcg_array(self.shape, dtype, 2)
+        oracle.sweep(self.a, self.b, self.offs, self.coefs, self.halo)     # warm-up / first touch
+        self.cores = oracle.lib().drs_oracle_threads()
+
+    def run(self, budget_s):
+        """Sweeps for about budget_s seconds -> (GStencil/s over the sample, seconds, sweeps)."""
+        used, sweeps = 0.0, 0
+        while used < budget_s or sweeps < 2:
+            t0 = time.perf_counter()
+            self.oracle.sweep(self.a, self.b, self.offs, self.coefs, self.halo)
+            used += time.perf_counter() - t0
+            sweeps += 1
+            self.a, self.b = self.b, self.a
+            if sweeps % 8 == 0:       # sum of coefficients > 1: keep the values finite
+                self.a *= 1e-3
+        return interior_points(self.shape, self.halo) * self.step * sweeps / used / 1e9, used, sweeps
+
+    def describe(self, sweeps, seconds):
+        return ("%s sub-grid %s (full-size planes, slow axis cut), composed %d-point operator (gold restatement, "
+                "%d timesteps per sweep), %d sweeps in %.1f s" % (self.workload, "x".join(map(str, self.shape)),
+                                                                   len(self.coefs), self.step, sweeps, seconds))
+
+
 def cpu_baseline(workload, budget_s=12.0):
-    """The oracle port on all host cores over a bounded sample of the workload."""
-    import numpy as np
-    from oracle import oracle
-    import drstencil_b200 as drs
-    from drstencil_b200.presets import PRESETS
-    path, kn = PRESETS[WORKLOADS[workload][0]]
-    is3d = os.path.basename(path)[3:].startswith("3d")
-    s = oracle.parse_stc(path, is3d)
-    step = kn.step
-    pts = oracle.compose(s.points, step)
-    offs, coefs = oracle.terms(pts)
-    halo, _ = oracle.order_dist(pts, s.dim)
-    dtype = np.float32 if kn.dtype == drs.F32 else np.float64
-    if is3d:
-        shape = (min(s.L, 256), min(s.M, 768), min(s.N, 768))
-    else:
-        shape = (min(s.M, 4096), s.N)
-    a = oracle.lcg_array(shape, dtype, 1)
-    b = oracle.lcg_array(shape, dtype, 2)
-    oracle.sweep(a, b, offs, coefs, halo)        # warm-up / first touch of b
-    t_used, best, sweeps = 0.0, None, 0
-    while t_used < budget_s and sweeps < 6:
-        t0 = time.perf_counter()
-        oracle.sweep(a, b, offs, coefs, halo)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-        t_used += dt
-        sweeps += 1
-        a, b = b, a
-    gst = interior_points(shape, halo) * step / best / 1e9
-    return {"value": gst, "unit": "GStencil/s", "cores": oracle.lib().drs_oracle_threads(), "kind": "port",
-            "sample": "%s sub-grid %s, composed %d-point operator (gold restatement, %d timesteps per sweep), best of %d sweeps"
-                      % (workload, "x".join(map(str, shape)), len(coefs), step, sweeps),
-            "seconds_per_sweep": best}
+    """bench.py's cpu_baseline object: about budget_s seconds of CPU work."""
+    cs = CpuSample(workload)
+    gst, used, sweeps = cs.run(budget_s)
+    return {"value": gst, "unit": "GStencil/s", "cores": cs.cores, "kind": "port",
+            "sample": cs.describe(sweeps, used), "seconds_per_sweep": used / sweeps}
 
 
 def reference_gpu_kernel(workload):
@@ -352,25 +369,30 @@ def per_config(args):
 
 def run_reference(args, rank):
     """Reference arm: the CPU oracle port (the reference ships no CPU loop and its emitted CUDA
-    is not a CPU implementation), all host threads, bounded sample per step."""
+    is not a CPU implementation), all host threads; each step is a bounded sample (~3 s of sweeps)
+    of the workload, W warm-up steps, K timed steps."""
     if rank != 0:
         return None
     wl = args.workload or "c5"
-    vals = []
-    base = None
-    for i in range(args.warmup + args.steps):
-        base = cpu_baseline(wl, budget_s=3.0)
-        if i >= args.warmup:
-            vals.append(base["value"])
-    v = sum(vals) / len(vals)
-    base["value"] = v
+    cs = CpuSample(wl)
+    for _ in range(args.warmup):
+        cs.run(3.0)
+    vals, secs, sweeps = [], 0.0, 0
+    for _ in range(max(1, args.steps)):
+        v, t, n = cs.run(3.0)
+        vals.append(v)
+        secs += t
+        sweeps += n
+    v = interior_points(cs.shape, cs.halo) * cs.step * sweeps / secs / 1e9
+    base = {"value": v, "unit": "GStencil/s", "cores": cs.cores, "kind": "port", "sample": cs.describe(sweeps, secs),
+            "seconds_per_sweep": secs / sweeps, "per_step": vals}
     preset, timesteps, desc = WORKLOADS[wl]
     return {"impl": "reference", "metric": "GStencil/s", "value": v, "unit": "GStencil/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds_per_sweep"] * 1e3,
-            "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
-            "dtype": "f64" if wl != "c3" else "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "strong" if wl == "c5" else "weak", "vs_baseline": None,
+            "dtype": "f64" if wl not in ("c3", "c3t2") else "f32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (wl, desc), "note": "CPU port of the reference's gold expression "
-                       "(the reference has no CPU implementation); each step = one bounded sample"},
+                       "(the reference has no CPU implementation); each step = one bounded sample of ~3 s"},
             "cpu_baseline": base, "gpu_launches": 0,
             "e2e": {"value": v, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
