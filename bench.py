@@ -256,7 +256,8 @@ def run_single(args, rank, world):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(info.kernel_name)
+        # keyed by workload (tools/make_profiles.py); --depth n swaps the kernel, for which there is no capture
+        traffic = json.load(open(tp)).get(wl if kn.step == PRESETS[preset][1].step else "")
     line = {
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
@@ -358,7 +359,7 @@ def per_config(args):
                                      "gstencil_roofline": peak / (2 * esize) * kn.step,
                                      "frac_of_single_step_gstencil_roofline": (upd / secs / 1e9) / (peak / (2 * esize)),
                                      "torch_copy_same_array_gbs": copy_gbs,
-                                     "traffic": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(info.kernel_name)
+                                     "traffic": (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wl)
                                                  if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")) else None)}})
             del A, B, plan
             torch.cuda.empty_cache()

@@ -649,6 +649,11 @@ int drs_gold_sweep(drs_plan* p, const void* d_in, void* d_out, void* stream) {
     return launch_gold(p, d_in, d_out, (cudaStream_t)stream);
 }
 
+static void drop_graphs(drs_plan* p) {
+    for (auto& g : p->graphs) cudaGraphExecDestroy(g.second.exec);
+    p->graphs.clear();
+}
+
 // The launch sequence of drs_run as an instantiated CUDA graph: built once per (A, B, sweep count) by
 // capturing the very same cuLaunchKernel calls on a private stream, replayed with one
 // cudaGraphLaunch.  Saves the per-launch gap between dependent kernels, which is what separates a
@@ -685,10 +690,7 @@ static bool run_graph(drs_plan* p, void* a, void* b, int n, cudaStream_t stream)
             cudaGetLastError(); p->use_graph = false; return false;
         }
         cudaGraphDestroy(g);
-        if (p->graphs.size() >= 16) {
-            for (auto& e : p->graphs) cudaGraphExecDestroy(e.second.exec);
-            p->graphs.clear();
-        }
+        if (p->graphs.size() >= 16) drop_graphs(p);
         it = p->graphs.emplace(key, drs_plan::RunGraph{exec, kernels}).first;
     }
     if (cudaGraphLaunch(it->second.exec, stream) != cudaSuccess) { cudaGetLastError(); p->use_graph = false; return false; }
@@ -922,6 +924,7 @@ int drs_plan_set_slab(drs_plan* p, long long global_slow, long long lo, long lon
     if (hi - lo + 2 * ghost != p->local_slow())
         return fail(DRS_E_ARG, "slab arrays must hold hi - lo + 2*Halo planes along the slow axis");
     p->slab = true; p->g_slow = global_slow; p->lo = lo; p->hi = hi;
+    drop_graphs(p);      // launch parameters changed
     return DRS_OK;
 }
 
@@ -936,6 +939,7 @@ int drs_plan_set_peers(drs_plan* p, void* const my_bases[2], void* const lower_b
         p->upper_bases[b] = upper_bases ? upper_bases[b] : nullptr;
     }
     p->lower_lo = lower_lo; p->upper_lo = upper_lo;
+    drop_graphs(p);      // launch parameters changed
     return DRS_OK;
 }
 

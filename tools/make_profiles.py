@@ -35,7 +35,7 @@ def main():
     out_dir = os.path.join(ROOT, "profiles")
     os.makedirs(out_dir, exist_ok=True)
     traffic_path = os.path.join(out_dir, "traffic.json")
-    traffic = {}          # rebuilt from this run's reports; the first report naming a kernel wins
+    traffic = {}          # workload -> DRAM bytes per launch, rebuilt from this run's reports
     summary = {}
     for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "*.ncu-rep"))):
         name = os.path.splitext(os.path.basename(rep))[0]
@@ -48,13 +48,14 @@ def main():
             continue
         keep = {k: s[k] for k in KEEP + ["kernel", "launches", "dram_bytes", "dram_gbs"] if k in s}
         summary[name] = keep
-        traffic.setdefault(s["kernel"], s.get("dram_bytes"))
+        # keyed by workload (prof_<workload>.ncu-rep): c4 and c4t2 share a kernel NAME but not a kernel
+        traffic[name.split("_", 1)[1] if "_" in name else name] = s.get("dram_bytes")
     for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "dram_*.csv"))):
         rows = metrics.parse(open(f).read())
         s = metrics.summarise(rows)
         if s:
             summary[os.path.splitext(os.path.basename(f))[0]] = {k: v for k, v in s.items() if not isinstance(v, dict)}
-            traffic.setdefault(s["kernel"], s.get("dram_bytes"))
+            traffic[os.path.splitext(os.path.basename(f))[0].split("_", 1)[1]] = s.get("dram_bytes")
     json.dump(summary, open(os.path.join(out_dir, "%s_ncu_summary.json" % tag), "w"), indent=1, sort_keys=True)
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
     # launch list of the bench command: per-kernel totals and shares
