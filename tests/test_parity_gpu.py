@@ -289,9 +289,10 @@ def test_degenerate_grids(built):
         assert np.array_equal(b.cpu().numpy(), ref), (name, shape)
 
 
-@pytest.mark.parametrize("preset,bar", [("c1", 0.0), ("c2", 1e-12), ("c3", 0.0), ("c4", 0.0)])
+@pytest.mark.parametrize("preset,bar", [("c1", 0.0), ("c2", 1e-12), ("c3", 0.0), ("c4", 0.0), ("c5", 0.0)])
 def test_baseline_sizes_against_the_gold_kernel(built, preset, bar):
-    """BASELINE.json sizes (4096^2, 16384^2 depth 4, 16384^2 fp32, 768^3): one sweep of the tuned
+    """BASELINE.json sizes (4096^2, 16384^2 depth 4, 16384^2 fp32, 768^3, and 1536^3 = 3.6e9 points, beyond
+    32-bit indexing: three 27 GiB arrays on one 180 GB GPU): one sweep of the tuned
     plan against the device gold kernel (itself bit-exact against the oracle at small sizes) --
     bit-identical for depth 1, <= 1e-12 relative for the temporally fused config."""
     import torch
