@@ -166,12 +166,14 @@ _KNOB_DEFAULTS = dict(step=1, dist=0, streaming=0, bx=16, by=16, sn=16, stream_u
 class Knobs:
     """The generator's options (main.cpp:12-56), same names, same defaults.  Only options passed
     explicitly constrain the engine; the rest are chosen for B200.  Engine-only tuning overrides:
-    stages, min_blocks, warps, rows_3d (RY), rows_per_stage, vectors (128-bit vectors per thread, 2D)."""
+    stages, min_blocks, warps, rows_3d (RY), rows_per_stage, vectors (128-bit vectors per thread, 2D),
+    share_x / share_y (experimental: warps of a CTA that share one input ring in the single-step 3D sweep)."""
 
     def __init__(self, **kw):
         self.values = dict(_KNOB_DEFAULTS)
         self.explicit = set()
-        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0, vectors=0, no_factor=0, no_fused3d=0)
+        self.extra = dict(stages=0, min_blocks=0, warps=0, rows_3d=0, rows_per_stage=0, vectors=0, no_factor=0, no_fused3d=0,
+                          share_x=0, share_y=0)
         for k, v in kw.items():
             self.set(k, v)
 
@@ -212,6 +214,8 @@ class Knobs:
         k.reserved[4] = self.extra["rows_per_stage"]
         k.reserved[5] = self.extra["vectors"]
         k.reserved[6] = (1 if self.extra["no_factor"] else 0) | (2 if self.extra["no_fused3d"] else 0)
+        if self.extra["share_x"] > 1 or self.extra["share_y"] > 1:      # experimental CTA-shared 3D ring
+            k.reserved[6] |= ((max(1, self.extra["share_x"]) - 1) & 3) << 2 | ((max(1, self.extra["share_y"]) - 1) & 3) << 4
         return k
 
     def __repr__(self):

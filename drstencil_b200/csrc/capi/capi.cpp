@@ -437,7 +437,7 @@ int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int 
     fill_params(p, in, out, q, ring, sub);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
     if (tiles <= 0) return DRS_OK;
-    const long long ctas = (tiles + p->spec.tiles_per_cta() - 1) / p->spec.tiles_per_cta();
+    const long long ctas = p->spec.ctas(q.nxs, q.nys, q.nzs);
     if (ctas > 0x7fffffffLL) return fail(DRS_E_ARG, "grid too large");
     void* args[] = {tm, &q};
     CUresult r = driver().LaunchKernel(p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
@@ -615,7 +615,7 @@ int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
     DevParams q;
     fill_params(p, nullptr, nullptr, q);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
-    info->grid_x = (int)((tiles + s.tiles_per_cta() - 1) / s.tiles_per_cta()); info->grid_y = 1; info->grid_z = 1;
+    info->grid_x = (int)(tiles > 0 ? s.ctas(q.nxs, q.nys, q.nzs) : 0); info->grid_y = 1; info->grid_z = 1;
     info->block = s.nw * 32;
     info->smem_bytes = s.tma_ok ? s.smem_bytes() : 0;
     info->regs_per_thread = p->regs; info->spill_bytes = p->spill;

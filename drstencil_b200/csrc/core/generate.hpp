@@ -39,6 +39,10 @@ struct KernelSpec {
     int base_order = 0;         // Halo of one sub-step
     // 3D `--step n` fused in one kernel (drs_sweep3d_t.cuh): a CTA of nw warps stacked along y
     bool fused3d = false;
+    // experimental (engine override share_x / share_y): single-step 3D sweep whose sx * sy warps share one
+    // input ring per CTA (drs_sweep3d_cta.cuh) instead of one private ring per warp
+    bool share3d = false;
+    int sx = 1, sy = 1;
     // row-factorised evaluation (temporal mode only): out = sum_dj w[dj] * H(row j+dj) + residual terms,
     // H(row)(x) = sum_di h[di] * u[row][x+di] computed once per row and reused by every output row
     bool factored = false;
@@ -56,19 +60,25 @@ struct KernelSpec {
     int cols() const { return (dim == 2 ? vt : 1) * vec(); }   // consecutive columns per thread
     int wt() const { return 32 * cols(); }
     int wu() const { return (dim == 2 || fused3d) ? wt() - 2 * hw() : wt(); }
-    int wb() const { return wt() + 2 * e0(); }
+    int wb() const { return (share3d ? sx * wt() : wt()) + 2 * e0(); }
     // 3D: rows of one tile (a warp's, or the whole CTA's when fused3d), rows it stores, rows of its TMA box
     int tile_rows() const { return fused3d ? nw * ry : ry; }
     int tile_rows_useful() const { return fused3d ? nw * ry - 2 * (ts - 1) * rj : ry; }
-    int box_rows() const { return tile_rows() + 2 * rj; }
+    int box_rows() const { return (share3d ? sy * ry : tile_rows()) + 2 * rj; }
     int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * box_rows() * esize(); }
     int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
     int smem_bytes() const {
         if (fused3d) return (st + 2 * (ts - 1)) * stage_stride() + st * 8;
+        if (share3d) return st * stage_stride() + 2 * st * 8;      // one ring, full + empty barriers
         return nw * st * stage_stride() + nw * st * 8;
     }
     // tiles handled by one CTA
     int tiles_per_cta() const { return fused3d ? 1 : nw; }
+    // CTAs of one launch over nxs x nys x nzs warp tiles
+    long long ctas(long long nxs, long long nys, long long nzs) const {
+        if (share3d) return ((nxs + sx - 1) / sx) * ((nys + sy - 1) / sy) * nzs;
+        return (nxs * nys * nzs + tiles_per_cta() - 1) / tiles_per_cta();
+    }
 };
 
 inline int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
@@ -223,6 +233,14 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     if (k.reserved[3] > 0 && s.dim == 3) s.ry = k.reserved[3];
     if (k.reserved[4] > 0 && s.dim == 2) s.rb = pow2_floor(k.reserved[4]);
     {
+        // reserved[6] bits 2-3 / 4-5: warps of a CTA along x / y that share one ring (value - 1); 0 = private rings
+        const int shx = ((k.reserved[6] >> 2) & 3) + 1, shy = ((k.reserved[6] >> 4) & 3) + 1;
+        if (s.dim == 3 && !s.fused3d && s.ts == 1 && shx * shy > 1) {
+            s.share3d = true; s.sx = shx; s.sy = shy; s.nw = shx * shy;
+            if (s.wb() > 256 || s.box_rows() > 256) return "shared tile exceeds the 256-element TMA box";
+        }
+    }
+    {
         // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
         // per SM is the most that budget allows (never forces spills)
         const int live = s.fused3d ? (s.ts * (2 * s.rk + 1) * s.ry * vec + 16) * (s.esize() / 4)
@@ -241,7 +259,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     if (s.chunk > slow_out) s.chunk = (int)slow_out;
     if (s.chunk < 1) s.chunk = 1;
-    while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d) s.nw /= 2;
+    while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d && !s.share3d) s.nw /= 2;
     while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
     if (s.smem_bytes() > 227 * 1024) return "tile does not fit in shared memory";
     // TMA needs 16-byte row pitch
@@ -420,6 +438,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_RK " << s.rk << "\n#define DRS_RJ " << s.rj << "\n#define DRS_E " << s.e << "\n";
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
+    if (s.share3d) o << "#define DRS_SX " << s.sx << "\n#define DRS_SY " << s.sy << "\n";
     // development aid: DRS_EXTRA_DEFINES="A=1;B=2" adds `#define A 1` ... to the translation unit
     // (tools/probe_shape.py experiments; part of the source, hence of the cubin cache key)
     if (const char* xd = std::getenv("DRS_EXTRA_DEFINES")) {
@@ -436,7 +455,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     if (s.fused3d) emit_scatter3(o, s);
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
     if (s.tma_ok)
-        o << "#include \"" << (s.fused3d ? "drs_sweep3d_t.cuh" : s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
+        o << "#include \"" << (s.fused3d ? "drs_sweep3d_t.cuh" : s.share3d ? "drs_sweep3d_cta.cuh" : s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
     o << "#include \"drs_gold.cuh\"\n";
     return o.str();
 }
