@@ -1,5 +1,5 @@
 // drs_sweep3d_cta.cuh -- single-step 3D sweep with ONE input ring per CTA (EXPERIMENTAL, opt-in:
-// engine override share_x / share_y; compiled and resource-checked, not yet measured on a GPU).
+// engine override share_x / share_y; bit-exact on B200 in tests/test_experimental_shared_ring.py, not yet timed).
 //
 // Same arithmetic, register queue and stores as drs_sweep3d.cuh (which stays the default and is not
 // touched by this file); what changes is who fetches the input.  There every warp owns a private

@@ -1,7 +1,7 @@
 """The CTA-shared input ring of the single-step 3D sweep (drs_sweep3d_cta.cuh; engine override
 share_x / share_y) is EXPERIMENTAL: it is compiled and resource-checked here on the CPU; its GPU
-parity cases run only with DRS_TEST_EXPERIMENTAL=1 until the variant has been measured and
-adopted (they are the first thing to run when it is picked up)."""
+parity cases (bit-exact on B200 when they were written) run only with DRS_TEST_EXPERIMENTAL=1 until
+the variant has been timed and adopted."""
 import os
 
 import numpy as np
