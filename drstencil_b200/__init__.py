@@ -96,6 +96,7 @@ def lib():
         "drs_plan_set_host_block": (i32, [vp, ll]),
         "drs_plan_set_graph": (i32, [vp, i32]),
         "drs_plan_host_schedule": (i32, [vp, i32, P(ll), i32]),
+        "drs_plan_slab_schedule": (i32, [vp, i32, i32, P(ll), i32]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -430,6 +431,15 @@ class Plan:
         buf = (ctypes.c_longlong * (5 * n))()
         _check(lib().drs_plan_host_schedule(self._h, iterations, buf, n))
         return [tuple(buf[5 * i:5 * i + 5]) for i in range(n)]
+
+    def slab_schedule(self, iterations: int, up_skew: bool):
+        """[(kind, block, sweep, lo, hi, faces)] for this rank of a slab run (planner only; see drstencil.h)."""
+        n = _check(lib().drs_plan_slab_schedule(self._h, iterations, int(up_skew), None, 0))
+        if n == 0:
+            return []
+        buf = (ctypes.c_longlong * (6 * n))()
+        _check(lib().drs_plan_slab_schedule(self._h, iterations, int(up_skew), buf, n))
+        return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
 
     def set_host_block(self, units: int) -> None:
         """Block thickness (slow-axis units) of the streamed run_host: 0 = auto, < 0 = plain sequence."""

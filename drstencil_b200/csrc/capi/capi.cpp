@@ -748,9 +748,9 @@ int drs_plan_sync_check(drs_plan* p, void* stream) {
 // Slow-axis units per block of the streamed host run, 0 = run the plain copy-sweep-copy sequence.
 // A block must be at least two halos thick (core/host_schedule.hpp); blocks of >= 32 MiB keep the
 // copy engines efficient, at most ~16 of them keep the number of small launches low.
-static long long host_block_units(const drs_plan* p, int sweeps) {
+static long long host_block_units(const drs_plan* p, int sweeps, bool allow_slab = false) {
     const drs::KernelSpec& s = p->spec;
-    if (p->host_block < 0 || p->slab || !s.tma_ok || s.sub_launches > 1 || sweeps <= 0) return 0;
+    if (p->host_block < 0 || (p->slab && !allow_slab) || !s.tma_ok || s.sub_launches > 1 || sweeps <= 0) return 0;
     const long long slow = p->local_slow(), H = s.halo;
     const double unit = (double)(s.dim == 3 ? p->st.M * p->st.N : p->st.N) * s.esize();
     long long S = p->host_block;
@@ -874,6 +874,34 @@ int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* devic
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (device_ms) *device_ms = ms;
     return rc != DRS_OK ? rc : rc2;
+}
+
+int drs_plan_slab_schedule(const drs_plan* p, int iterations, int up_skew, long long* records6, int capacity) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    if (!p->slab) return fail(DRS_E_ARG, "call drs_plan_set_slab first");
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    const long long S = host_block_units(p, n, true);
+    if (S <= 0) return 0;
+    const long long H = p->spec.halo, org = p->lo - H;
+    drs::SlabSide g;
+    g.local = p->local_slow();
+    g.own_lo = H; g.own_hi = g.local - H;
+    g.out_lo = std::max<long long>(p->lo, H) - org;
+    g.out_hi = std::min<long long>(p->hi, p->g_slow - H) - org;
+    g.has_lower = p->lo > 0; g.has_upper = p->hi < p->g_slow;
+    g.up_skew = up_skew != 0;
+    if (g.out_hi - g.out_lo < 2 * H || g.own_hi - g.own_lo <= S) return 0;
+    const std::vector<drs::SlabStep> steps = drs::plan_slab_schedule(g, H, S, n);
+    if (records6) {
+        if (capacity < (int)steps.size()) return fail(DRS_E_ARG, "buffer too small");
+        for (size_t i = 0; i < steps.size(); ++i) {
+            const drs::SlabStep& st = steps[i];
+            long long* r = records6 + 6 * i;
+            r[0] = st.kind; r[1] = st.block; r[2] = st.sweep; r[3] = st.lo; r[4] = st.hi; r[5] = st.faces;
+        }
+    }
+    return (int)steps.size();
 }
 
 int drs_plan_set_graph(drs_plan* p, int enable) {

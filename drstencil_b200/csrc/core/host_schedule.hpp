@@ -69,4 +69,105 @@ inline HostSchedule plan_host_schedule(long long slow, long long H, long long S,
     return hs;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same block order for ONE RANK of a slab-decomposed run (planner only: the executor that would
+// drive it with the slab flags is not written yet; tests/test_slab_schedule.py runs the step lists
+// of all ranks against each other on the CPU, with random interleavings, ghost planes and flags).
+//
+// Local plane indices: the rank's array holds `local` planes, of which [own_lo, own_hi) are its own
+// (host slab, uploaded / downloaded) and [out_lo, out_hi) are swept (out_lo > own_lo only where the
+// global frozen ring lies inside the slab); the rest are ghost planes a neighbour fills.
+//
+// A face to a neighbour is fixed in space, so the blocks cannot slide past it: neighbouring ranks
+// skew in OPPOSITE directions (even ranks down, odd ranks up, processing their blocks top-down).
+// Then the two blocks that meet at a face are both processed first, or both processed last, and run
+// their sweeps in lockstep through the existing step flags:
+//   wait   before a launch that reads ghost planes of a face: flag of that face >= sweep
+//          (the neighbour has produced -- and pushed -- level sweep-1, and has finished reading what
+//          this launch's own push will overwrite);
+//   signal after the launch that completes the face planes of a level: flag := sweep + 1;
+//   init   after the upload that brings the face planes of level 0: push them to the neighbour's
+//          ghost, flag := 1.
+// When a block's range has slid off a face the next block inherits the lockstep at the same sweep on
+// both sides (mirror symmetry), so no rank ever waits for a level its neighbour produces later than
+// it needs it itself.
+struct SlabSide {
+    long long local, own_lo, own_hi, out_lo, out_hi;
+    bool has_lower, has_upper;   // neighbours below / above
+    bool up_skew;                // mirror image: blocks processed top-down, ranges slide up
+};
+
+enum HostFace {
+    WAIT_LOWER = 1, WAIT_UPPER = 2, SIGNAL_LOWER = 4, SIGNAL_UPPER = 8, INIT_LOWER = 16, INIT_UPPER = 32
+};
+
+struct SlabStep : HostStep { int faces; };
+
+inline std::vector<SlabStep> plan_slab_schedule(SlabSide g, long long H, long long S, int n) {
+    const long long L = g.local;
+    if (g.up_skew) {            // plan the mirror image, reflect the result
+        SlabSide m = g;
+        m.up_skew = false;
+        m.own_lo = L - g.own_hi; m.own_hi = L - g.own_lo;
+        m.out_lo = L - g.out_hi; m.out_hi = L - g.out_lo;
+        m.has_lower = g.has_upper; m.has_upper = g.has_lower;
+        std::vector<SlabStep> r = plan_slab_schedule(m, H, S, n);
+        for (SlabStep& st : r) {
+            const long long lo = L - st.hi, hi = L - st.lo;
+            st.lo = lo; st.hi = hi;
+            const int f = st.faces;
+            st.faces = ((f & WAIT_LOWER) ? WAIT_UPPER : 0) | ((f & WAIT_UPPER) ? WAIT_LOWER : 0) |
+                       ((f & SIGNAL_LOWER) ? SIGNAL_UPPER : 0) | ((f & SIGNAL_UPPER) ? SIGNAL_LOWER : 0) |
+                       ((f & INIT_LOWER) ? INIT_UPPER : 0) | ((f & INIT_UPPER) ? INIT_LOWER : 0);
+        }
+        return r;
+    }
+    S = std::max<long long>(S, std::max<long long>(2 * H, 1));
+    const long long thin = std::max<long long>(2 * H, std::max<long long>(S / 4, 1));
+    std::vector<long long> edge;
+    edge.push_back(g.own_lo);
+    long long at = std::min(g.own_lo + thin, g.own_hi);
+    while (at < g.own_hi) {
+        edge.push_back(at);
+        const long long left = g.own_hi - at;
+        at += (left - thin > S) ? S : ((left > 2 * thin) ? left - thin : left);
+    }
+    edge.push_back(g.own_hi);
+    const int B = (int)edge.size() - 1;
+    auto cut = [&](int b, int s) -> long long {
+        if (b <= 0) return g.out_lo;
+        if (b >= B) return g.out_hi;
+        return std::min(std::max(edge[b] - (long long)s * H, g.out_lo), g.out_hi);
+    };
+    std::vector<SlabStep> steps;
+    for (int b = 0; b < B; ++b) {
+        SlabStep up{};
+        up.kind = HostStep::UPLOAD; up.block = b; up.sweep = 0; up.lo = edge[b]; up.hi = edge[b + 1];
+        up.faces = (g.has_lower && b == 0 ? INIT_LOWER : 0) | (g.has_upper && b == B - 1 ? INIT_UPPER : 0);
+        steps.push_back(up);
+        for (int s = 1; s <= n; ++s) {
+            const long long lo = cut(b, s), hi = cut(b + 1, s);
+            if (hi <= lo) continue;
+            SlabStep sw{};
+            sw.kind = HostStep::SWEEP; sw.block = b; sw.sweep = s; sw.lo = lo; sw.hi = hi;
+            if (g.has_lower && lo < g.own_lo + H) {
+                sw.faces |= WAIT_LOWER;
+                if (hi >= g.own_lo + H) sw.faces |= SIGNAL_LOWER;    // completes the face planes of level s
+            }
+            if (g.has_upper && hi > g.own_hi - H) {
+                sw.faces |= WAIT_UPPER;
+                if (lo <= g.own_hi - H) sw.faces |= SIGNAL_UPPER;
+            }
+            steps.push_back(sw);
+        }
+        SlabStep dn{};
+        dn.kind = HostStep::DOWNLOAD; dn.block = b; dn.sweep = 0;
+        dn.lo = b == 0 ? g.own_lo : cut(b, n);
+        dn.hi = std::max(dn.lo, b == B - 1 ? g.own_hi : cut(b + 1, n));
+        dn.faces = 0;
+        steps.push_back(dn);
+    }
+    return steps;
+}
+
 }  // namespace drs

@@ -161,6 +161,14 @@ int drs_plan_set_host_block(drs_plan *p, long long units);
  * the slow-axis range copied / produced; per block: its upload, its sweeps, its download.  Returns the
  * number of records (pass NULL to query), 0 when the plain sequence would run. */
 int drs_plan_host_schedule(const drs_plan *p, int iterations, long long *records5, int capacity);
+/* PLANNER ONLY (no executor yet): the step list one rank of a slab-decomposed host-buffer run would execute so
+ * that its copies overlap its sweeps like drs_run_host does on one GPU.  The plan must be a slab
+ * (drs_plan_set_slab); up_skew = 0 for even ranks (blocks bottom-up, ranges sliding down), 1 for odd ranks (the
+ * mirror image), so that the blocks meeting at a face run in lockstep.  Records of six values {kind, block, sweep,
+ * lo, hi, faces}, local plane indices; faces is a bit set: 1 / 2 wait for the lower / upper neighbour's flag
+ * >= sweep before the launch, 4 / 8 signal sweep + 1 to it afterwards, 16 / 32 (uploads) push the level-0 face
+ * planes to it and signal 1.  Returns the number of records (NULL to query), 0 when the plain sequence applies. */
+int drs_plan_slab_schedule(const drs_plan *p, int iterations, int up_skew, long long *records6, int capacity);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
 int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);
