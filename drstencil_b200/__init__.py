@@ -97,6 +97,7 @@ def lib():
         "drs_plan_set_graph": (i32, [vp, i32]),
         "drs_plan_host_schedule": (i32, [vp, i32, P(ll), i32]),
         "drs_plan_slab_schedule": (i32, [vp, i32, i32, P(ll), i32]),
+        "drs_run_host_slab": (i32, [vp, vp, i32, i32, vp, vp, vp, ll, P(ctypes.c_float)]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -440,6 +441,14 @@ class Plan:
         buf = (ctypes.c_longlong * (6 * n))()
         _check(lib().drs_plan_slab_schedule(self._h, iterations, int(up_skew), buf, n))
         return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
+
+    def run_host_slab(self, h_own, iterations: int, up_skew: bool, my_flags: int, lower_flag: int, upper_flag: int,
+                      flag_base: int) -> float:
+        """EXPERIMENTAL: this rank's share of a slab-decomposed host-buffer run (see drstencil.h); device ms."""
+        ms = ctypes.c_float()
+        _check(lib().drs_run_host_slab(self._h, _ptr(h_own), iterations, int(up_skew), my_flags, lower_flag or None,
+                                       upper_flag or None, flag_base, ctypes.byref(ms)))
+        return ms.value
 
     def set_host_block(self, units: int) -> None:
         """Block thickness (slow-axis units) of the streamed run_host: 0 = auto, < 0 = plain sequence."""

@@ -876,13 +876,10 @@ int drs_run_host(drs_plan* p, void* h_a, void* h_b, int iterations, float* devic
     return rc != DRS_OK ? rc : rc2;
 }
 
-int drs_plan_slab_schedule(const drs_plan* p, int iterations, int up_skew, long long* records6, int capacity) {
-    if (!p) return fail(DRS_E_ARG, "null plan");
-    if (!p->slab) return fail(DRS_E_ARG, "call drs_plan_set_slab first");
-    int n = 0;
-    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+// Step list of this rank for a slab host run; empty when the plain sequence applies.
+static std::vector<drs::SlabStep> slab_steps(const drs_plan* p, int n, bool up_skew) {
     const long long S = host_block_units(p, n, true);
-    if (S <= 0) return 0;
+    if (S <= 0) return {};
     const long long H = p->spec.halo, org = p->lo - H;
     drs::SlabSide g;
     g.local = p->local_slow();
@@ -890,9 +887,18 @@ int drs_plan_slab_schedule(const drs_plan* p, int iterations, int up_skew, long 
     g.out_lo = std::max<long long>(p->lo, H) - org;
     g.out_hi = std::min<long long>(p->hi, p->g_slow - H) - org;
     g.has_lower = p->lo > 0; g.has_upper = p->hi < p->g_slow;
-    g.up_skew = up_skew != 0;
-    if (g.out_hi - g.out_lo < 2 * H || g.own_hi - g.own_lo <= S) return 0;
-    const std::vector<drs::SlabStep> steps = drs::plan_slab_schedule(g, H, S, n);
+    g.up_skew = up_skew;
+    if (g.out_hi - g.out_lo < 2 * H || g.own_hi - g.own_lo <= S) return {};
+    return drs::plan_slab_schedule(g, H, S, n);
+}
+
+int drs_plan_slab_schedule(const drs_plan* p, int iterations, int up_skew, long long* records6, int capacity) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    if (!p->slab) return fail(DRS_E_ARG, "call drs_plan_set_slab first");
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    const std::vector<drs::SlabStep> steps = slab_steps(p, n, up_skew != 0);
+    if (steps.empty()) return 0;
     if (records6) {
         if (capacity < (int)steps.size()) return fail(DRS_E_ARG, "buffer too small");
         for (size_t i = 0; i < steps.size(); ++i) {
@@ -991,6 +997,111 @@ int drs_wait_flags(drs_plan* p, const void* my_flags, int wait_lower, int wait_u
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch wait_: " + cu_err(r));
     p->launches++;
     return DRS_OK;
+}
+
+// EXPERIMENTAL executor of drs_plan_slab_schedule (written against the CPU-verified planner; not yet run on
+// GPUs -- nothing in the package or the bench calls it).  One rank's share of a slab-decomposed host-buffer
+// run: h_own holds the rank's own planes; uploads, sweeps and downloads run on three streams chained by
+// events as in run_host_streamed; launches that touch a face are bracketed by the slab flag kernels, and the
+// upload that brings a face's level-0 planes is followed by a peer copy of them into the neighbour's ghosts.
+// Flags are monotone: this call uses the values flag_base + 1 ... flag_base + sweeps + 1; the caller separates
+// calls by a barrier and advances flag_base by at least sweeps + 2.
+int drs_run_host_slab(drs_plan* p, void* h_own, int iterations, int up_skew, const void* my_flags, void* lower_flag,
+                      void* upper_flag, long long flag_base, float* device_ms) {
+    if (!p || !h_own || !my_flags) return fail(DRS_E_ARG, "null argument");
+    if (!p->slab || !p->my_bases[0] || !p->my_bases[1]) return fail(DRS_E_ARG, "call drs_plan_set_slab and drs_plan_set_peers first");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    const std::vector<drs::SlabStep> steps = slab_steps(p, n, up_skew != 0);
+    if (steps.empty()) return fail(DRS_E_ARG, "no streamed schedule for this slab (too thin, or switched off): use the plain sequence");
+    const long long H = p->spec.halo, local = p->local_slow(), org = p->lo - H;
+    const size_t unit = (size_t)(p->spec.dim == 3 ? p->st.M * p->st.N : p->st.N) * p->spec.esize();
+    for (cudaStream_t* st : {&p->hs_up, &p->hs_run, &p->hs_dn})
+        if (!*st && cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) != cudaSuccess)
+            return fail(DRS_E_CUDA, "cudaStreamCreate failed");
+    char* dA = (char*)p->my_bases[0];
+    char* dB = (char*)p->my_bases[1];
+    char* hA = (char*)h_own;
+    int B = 0;
+    for (const drs::SlabStep& st : steps) B = std::max(B, st.block + 1);
+    std::vector<cudaEvent_t> up(B), done(B);
+    cudaEvent_t e0, e1, fin;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventCreateWithFlags(&fin, cudaEventDisableTiming);
+    for (int b = 0; b < B; ++b) {
+        cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+    }
+    auto signal = [&](cudaStream_t st, bool lo, bool hi, long long value) -> int {
+        void* lf = lo ? lower_flag : nullptr;
+        void* uf = hi ? upper_flag : nullptr;
+        void* args[] = {&lf, &uf, &value};
+        CUresult r = driver().LaunchKernel(p->f_signal, 1, 1, 1, 32, 1, 1, 0, (CUstream)st, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch signal_: " + cu_err(r));
+        p->launches++;
+        return DRS_OK;
+    };
+    cudaEventRecord(e0, 0);
+    for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamWaitEvent(st, e0, 0);
+    // uploads (own planes: host index = local index - H), each followed by the level-0 ghost push it enables
+    for (const drs::SlabStep& st : steps) {
+        if (st.kind != drs::HostStep::UPLOAD || rc != DRS_OK) continue;
+        cudaMemcpyAsync(dA + st.lo * unit, hA + (st.lo - H) * unit, (size_t)(st.hi - st.lo) * unit, cudaMemcpyHostToDevice, p->hs_up);
+        if ((st.faces & drs::INIT_LOWER) && p->lower_bases[0]) {
+            // my planes [H, 2H) are the lower neighbour's upper ghost: same plane shift as the kernel's push
+            const long long shift = org - (p->lower_lo - H);
+            cudaMemcpyAsync((char*)p->lower_bases[0] + (H + shift) * unit, dA + H * unit, (size_t)H * unit, cudaMemcpyDefault, p->hs_up);
+            rc = signal(p->hs_up, true, false, flag_base + 1);
+        }
+        if ((st.faces & drs::INIT_UPPER) && p->upper_bases[0] && rc == DRS_OK) {
+            const long long shift = org - (p->upper_lo - H);
+            cudaMemcpyAsync((char*)p->upper_bases[0] + (local - 2 * H + shift) * unit, dA + (local - 2 * H) * unit, (size_t)H * unit,
+                            cudaMemcpyDefault, p->hs_up);
+            rc = signal(p->hs_up, false, true, flag_base + 1);
+        }
+        cudaEventRecord(up[st.block], p->hs_up);
+    }
+    for (const drs::SlabStep& st : steps) {
+        if (rc != DRS_OK) break;
+        if (st.kind == drs::HostStep::UPLOAD) {
+            cudaStreamWaitEvent(p->hs_run, up[st.block], 0);
+        } else if (st.kind == drs::HostStep::SWEEP) {
+            const bool wl = st.faces & drs::WAIT_LOWER, wu = st.faces & drs::WAIT_UPPER;
+            if (wl || wu) {
+                int a = wl, b = wu;
+                long long value = flag_base + st.sweep;
+                void* args[] = {(void*)&my_flags, &a, &b, &value, &p->d_fault};
+                CUresult r = driver().LaunchKernel(p->f_wait, 1, 1, 1, 32, 1, 1, 0, (CUstream)p->hs_run, args, nullptr);
+                if (r != CUDA_SUCCESS) { rc = fail(DRS_E_CUDA, "launch wait_: " + cu_err(r)); break; }
+                p->launches++;
+            }
+            const SlowRange r = {st.lo, st.hi};
+            rc = (st.sweep & 1) ? launch_one(p, dA, dB, p->hs_run, -1, &r) : launch_one(p, dB, dA, p->hs_run, -1, &r);
+            if (rc == DRS_OK && (st.faces & (drs::SIGNAL_LOWER | drs::SIGNAL_UPPER)))
+                rc = signal(p->hs_run, st.faces & drs::SIGNAL_LOWER, st.faces & drs::SIGNAL_UPPER, flag_base + st.sweep + 1);
+        } else {
+            cudaEventRecord(done[st.block], p->hs_run);
+            cudaStreamWaitEvent(p->hs_dn, done[st.block], 0);
+            if (st.hi > st.lo)
+                cudaMemcpyAsync(hA + (st.lo - H) * unit, dA + st.lo * unit, (size_t)(st.hi - st.lo) * unit, cudaMemcpyDeviceToHost, p->hs_dn);
+        }
+    }
+    cudaEventRecord(fin, p->hs_dn);
+    cudaStreamWaitEvent(0, fin, 0);
+    cudaEventRecord(e1, 0);
+    int rc2 = drs_plan_sync_check(p, nullptr);
+    for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn}) cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(fin);
+    for (int b = 0; b < B; ++b) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); }
+    if (device_ms) *device_ms = ms;
+    const cudaError_t ce = cudaGetLastError();
+    if (rc == DRS_OK && rc2 == DRS_OK && ce != cudaSuccess)
+        return fail(DRS_E_CUDA, std::string("streamed slab run: ") + cudaGetErrorString(ce));
+    return rc != DRS_OK ? rc : rc2;
 }
 
 int drs_ipc_export(void* d_ptr, unsigned char handle[64]) {

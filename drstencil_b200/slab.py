@@ -250,6 +250,32 @@ class GpuSlab:
     def run(self, timesteps: int) -> int:
         return self.runner.run(timesteps, self.step)
 
+    def run_host(self, h_own, timesteps: int) -> float:
+        """EXPERIMENTAL (not yet validated on GPUs): the reference schedule on this rank's HOST slab `h_own`
+        (own planes only, pinned), uploads / sweeps / downloads overlapped by time-skewed blocks, faces in
+        lockstep with the neighbours (drs_run_host_slab).  Needs the "p2p" halo mode and a GpuSlab of its
+        own: run() and run_host() number the step flags differently and must not be mixed on one object.
+        Returns device ms."""
+        import torch
+        import torch.distributed as dist
+        if self.mode != "p2p" or self.world < 2:
+            raise ValueError("run_host needs the p2p halo mode and at least two ranks (one GPU: Plan.run_host)")
+        if self.runner.sweeps_done:
+            raise ValueError("this GpuSlab has been used with run(); create a separate one for run_host()")
+        n = 0
+        t = 0
+        while t < timesteps:
+            n += 2
+            t += 2 * self.step
+        self.plan.sync_check()
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)               # nobody still reads ghosts of the previous call
+        base = getattr(self, "_flag_base", 0)
+        ms = self.plan.run_host_slab(h_own, timesteps, self.rank % 2 == 1, self._flags.ptr, self._lower_flag,
+                                     self._upper_flag, base)
+        self._flag_base = base + n + 2
+        return ms
+
     def owned(self, which: int = 0):
         """The rank's owned planes of buffer `which` (0 = A, where the result lands)."""
         g = self.geom

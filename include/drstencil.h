@@ -169,6 +169,13 @@ int drs_plan_host_schedule(const drs_plan *p, int iterations, long long *records
  * >= sweep before the launch, 4 / 8 signal sweep + 1 to it afterwards, 16 / 32 (uploads) push the level-0 face
  * planes to it and signal 1.  Returns the number of records (NULL to query), 0 when the plain sequence applies. */
 int drs_plan_slab_schedule(const drs_plan *p, int iterations, int up_skew, long long *records6, int capacity);
+/* EXPERIMENTAL executor of that step list (not yet validated on GPUs; nothing in the package calls it): this
+ * rank's share of a slab-decomposed host-buffer run.  h_own = the rank's own planes (pinned for overlap), result
+ * written back in place; the device arrays are the ones given to drs_plan_set_peers (second one zero-initialised
+ * by the caller); my_flags / lower_flag / upper_flag as for drs_wait_flags / drs_signal_peers.  Flag values used:
+ * flag_base + 1 ... flag_base + sweeps + 1 -- separate calls by a barrier and advance flag_base by sweeps + 2. */
+int drs_run_host_slab(drs_plan *p, void *h_own, int iterations, int up_skew, const void *my_flags, void *lower_flag,
+                      void *upper_flag, long long flag_base, float *device_ms);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
 int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);

@@ -12,6 +12,48 @@ import drstencil_b200 as drs
 from drstencil_b200.slab import GpuSlab
 
 
+def experimental_host_slabs(rank, world):
+    """Opt-in (DRS_TEST_EXPERIMENTAL=1): GpuSlab.run_host -- the streamed host-buffer run of a slab-decomposed
+    grid -- against the undecomposed single-GPU run, two calls in a row (flag bases carry over)."""
+    ok = True
+    for name, shape, kn, timesteps, block in [
+        ("3d7pt_star", (24 * world, 40, 128), dict(), 8, 6),
+        ("3d7pt_star", (30 * world + 1, 33, 66), dict(sn=5, rows_3d=4), 20, 4),
+        ("3d7pt_star", (32 * world, 44, 130), dict(step=2, sn=9), 8, 8),
+    ]:
+        path = os.path.join(ROOT, "stc", name + ".stc")
+        L, M, N = shape
+        g = torch.Generator(device="cuda")
+
+        def plane(zg):
+            g.manual_seed(99 + zg)
+            return torch.rand((M, N), dtype=torch.float64, device="cuda", generator=g)
+
+        st = drs.Stencil.from_file(path).set_size(shape)
+        plan = drs.Plan(st, drs.Knobs(**kn))
+        A = torch.stack([plane(z) for z in range(L)])
+        B = torch.zeros_like(A)
+        plan.run(A, B, timesteps)
+        plan.sync_check()
+        slab = GpuSlab(path, drs.Knobs(**kn), rank, world, halo="p2p", global_shape=shape)
+        slab.plan.set_host_block(block)
+        lo, hi = slab.geom.lo, slab.geom.hi
+        same = True
+        for call in range(2):
+            h = torch.stack([plane(z) for z in range(lo, hi)]).cpu().pin_memory()
+            slab.run_host(h, timesteps)
+            same = same and bool(torch.equal(h.cuda(), A[lo:hi]))
+        t = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("slab_check run_host %s %s %s block=%d world=%d -> %s" % (name, shape, kn, block, world,
+                                                                             "bit-exact" if int(t) else "MISMATCH"), flush=True)
+        ok = ok and bool(int(t))
+        slab.close()
+        dist.barrier()
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -60,6 +102,8 @@ def main():
             ok = ok and bool(int(t))
             slab.close()
             dist.barrier()
+    if os.environ.get("DRS_TEST_EXPERIMENTAL") == "1":
+        ok = experimental_host_slabs(rank, world) and ok
     if rank == 0:
         print("SLAB_CHECK_OK" if ok else "SLAB_CHECK_FAILED", flush=True)
     dist.destroy_process_group()
