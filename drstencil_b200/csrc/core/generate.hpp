@@ -240,6 +240,14 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
             if (s.wb() > 256 || s.box_rows() > 256) return "shared tile exceeds the 256-element TMA box";
         }
     }
+    if (s.fused3d) {
+        // knobs are hints: a band that does not fit the shared memory (e.g. --block-merge-y 2 at depth 4, where
+        // the reference happily emits a program) is thinned until it does -- rows per thread first, then warps
+        if (s.st < 2) s.st = 2;
+        while (s.smem_bytes() > 227 * 1024 && s.ry > 1) s.ry = std::max(1, s.ry / 2);
+        while (s.smem_bytes() > 227 * 1024 && s.st > 2) s.st /= 2;
+        while (s.smem_bytes() > 227 * 1024 && s.nw > 2 && (s.nw / 2) * s.ry - 2 * (s.ts - 1) * s.rj >= 1) s.nw /= 2;
+    }
     {
         // register budget: the window / queue plus working set; __launch_bounds__ minimum blocks
         // per SM is the most that budget allows (never forces spills)

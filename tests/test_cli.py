@@ -38,8 +38,12 @@ ARGVS = [
 ]
 
 
-def _run(binary, argv, cwd):
-    r = subprocess.run([binary] + argv, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+def _run(binary, argv, cwd, timeout=60):
+    try:
+        r = subprocess.run([binary] + argv, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                           timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return "timeout", ""
     return r.returncode, r.stdout
 
 
@@ -117,3 +121,68 @@ def test_cli_run_mode_on_gpu(built, tmp_path):
     assert rc == 0, out
     assert "GPU computation time:" in out and "[Test] RMS Error:" in out
     assert float(re.search(r"\[Test\] Max Error : (\S+)", out).group(1)) < 1e-12
+
+
+_VALUED = ["--step", "--dist", "--bx", "--by", "--sn", "--stream-unroll", "--block-merge-x", "--block-merge-y",
+           "--cyclic-merge-x", "--cyclic-merge-y", "--merge-forward"]
+_FLAGS = ["--streaming", "--prefetch", "--check", "--gold", "--3d"]
+
+
+def _random_argv(rng):
+    """Random command lines from the reference's option grammar, including malformed ones (a valued option
+    without its value, unknown options, `-o` with and without a file name, non-numeric and non-positive
+    values).  Left out on purpose: `--step` < 1 (the reference segfaults) and a 3D description parsed without
+    `--3d` (the reference never returns: its token loop spins on the fourth column)."""
+    argv = []
+    for _ in range(rng.randint(0, 6)):
+        k = rng.random()
+        if k < 0.55:
+            opt = rng.choice(_VALUED)
+            val = rng.choice(["1", "2", "3", "4"] if opt == "--step" else
+                             ["1", "2", "3", "4", "8", "16", "32", "64", "128", "0", "-1", "x", "256"])
+            argv += [opt, val] if rng.random() < 0.93 else [opt]
+        elif k < 0.85:
+            argv.append(rng.choice(_FLAGS))
+        elif k < 0.92:
+            argv += ["-o", rng.choice(["out.cu", "k.cu"])] if rng.random() < 0.8 else ["-o"]
+        else:
+            argv.append(rng.choice(["--bogus", "-x", "--help", "-h", "foo"]))
+    name = rng.choice(SHIPPED)
+    if name.startswith("3d") and "--3d" not in argv:
+        argv.insert(rng.randint(0, len(argv)), "--3d")
+    if rng.random() < 0.95:
+        argv.append(name + ".stc")
+    return argv
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/drstencil_ref not built")
+def test_random_command_lines_against_the_reference_binary(built, tmp_path):
+    """Differential test: 250 seeded random command lines give the same exit code, the same first line
+    of output and the same set of emitted files as the reference binary."""
+    import random
+    for d in ("ours", "ref"):
+        os.makedirs(tmp_path / d)
+        for name in SHIPPED:
+            shutil.copy(os.path.join(ROOT, "stc", name + ".stc"), tmp_path / d)
+    rng = random.Random(20240)
+    first = lambda s: (s.strip().splitlines() or [""])[0]
+    hung_or_crashed = []
+    for _ in range(250):
+        argv = _random_argv(rng)
+        rc_o, out_o = _run(CLI, argv, tmp_path / "ours", timeout=20)
+        rc_r, out_r = _run(REF, argv, tmp_path / "ref", timeout=5)
+        made_o = {f for f in os.listdir(tmp_path / "ours") if not f.endswith(".stc")}     # `-o --3d` names a file "--3d"
+        made_r = {f for f in os.listdir(tmp_path / "ref") if not f.endswith(".stc")}
+        for f in made_o:
+            os.remove(tmp_path / "ours" / f)
+        for f in made_r:
+            os.remove(tmp_path / "ref" / f)
+        assert rc_o != "timeout", argv
+        if rc_r == "timeout" or (isinstance(rc_r, int) and rc_r < 0):
+            hung_or_crashed.append(argv)         # the reference spins or dies on this input: nothing to compare
+            continue
+        assert rc_o == rc_r, (argv, rc_o, rc_r, out_o, out_r)
+        assert made_o == made_r, (argv, made_o, made_r)
+        if not (argv and argv[0] in ("--help", "-h")):
+            assert first(out_o) == first(out_r), (argv, out_o, out_r)
+    assert len(hung_or_crashed) <= 10, hung_or_crashed
