@@ -269,9 +269,14 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     if (s.chunk < 1) s.chunk = 1;
     while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d && !s.share3d) s.nw /= 2;
     while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
-    if (s.smem_bytes() > 227 * 1024) return "tile does not fit in shared memory";
     // TMA needs 16-byte row pitch
     s.tma_ok = (st.N % vec) == 0;
+    if (s.smem_bytes() > 227 * 1024) {
+        // e.g. a radius-3 3D operator composed three times (radius 9: a ring of 32 planes): the reference still
+        // emits a program for it, so the plan falls back to the naive one-thread-per-point kernel instead of failing
+        s.tma_ok = false;
+        s.note = "operator too deep for the shared-memory plane ring: naive kernel used";
+    }
     return "";
 }
 
