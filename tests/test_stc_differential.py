@@ -90,3 +90,61 @@ def test_random_descriptions_parse_and_analyse_like_the_reference(built, tmp_pat
         for r, o in pairs.items():
             assert theirs.get(r) == mine.get(o), (seed, argv, r, theirs.get(r), mine.get(o), text)
     assert compared >= 150 and emitted >= 60, (compared, emitted)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/drstencil_ref not built")
+def test_random_descriptions_compose_like_the_reference(built, tmp_path):
+    """The gold expression the reference emits (`--check`) for random descriptions and steps: term order,
+    offsets and the 6-significant-digit coefficient literals, plus the Halo / Dist / Range macros -- against
+    BOTH the oracle's restatement (oracle/oracle.py) and the product's C ABI (drs_stencil_compose / _terms /
+    _term_text / _analyze).  Many-digit coefficients (0.3333333 composed three times) exercise the literal
+    round trip (/root/reference/drstencil_2d.hpp:174,231-251)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_golden import parse_emitted
+    import drstencil_b200 as drs
+    from oracle import oracle
+    checked = 0
+    for seed in range(1000, 1120):
+        rng = random.Random(seed)
+        is3d = rng.random() < 0.4
+        text, _ = random_stc(rng, is3d)
+        (tmp_path / "t.stc").write_text(text)
+        step = rng.choice([1, 2, 2, 3])
+        dist = rng.choice([0, 0, 1, 2])
+        mf = rng.choice([5, 5, 1, 9])
+        argv = (["--3d"] if is3d else []) + ["--step", str(step), "--merge-forward", str(mf)] + \
+            (["--dist", str(dist)] if dist else []) + ["--streaming", "--bx", "256", "--sn", "64", "--check", "-o", "r.cu", "t.stc"]
+        if os.path.exists(tmp_path / "r.cu"):
+            os.remove(tmp_path / "r.cu")
+        try:
+            ref = subprocess.run([REF] + argv, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=5)
+        except subprocess.TimeoutExpired:
+            continue
+        # oracle restatement
+        s = oracle.parse_stc(str(tmp_path / "t.stc"), is3d)
+        pts = oracle.compose(s.points, step)
+        halo, d = oracle.order_dist(pts, s.dim, dist)
+        part = oracle.partition(pts, s.dim, d, mf)
+        # product
+        st = drs.Stencil.from_file(str(tmp_path / "t.stc"), is3d).compose(step)
+        if ref.returncode == 1:
+            assert "No data to reuse" in ref.stdout and part is None, (seed, text)
+            with pytest.raises(drs.DrsError):
+                st.analyze(dist, mf)
+            continue
+        if ref.returncode != 0:
+            continue                        # "Invalid configuration!" depends on the tile, not on the operator
+        macros, terms = parse_emitted(open(tmp_path / "r.cu").read(), is3d)
+        keys = sorted(pts)
+        assert [list(k) for k in keys] == [t[:3] for t in terms], (seed, text)
+        assert [oracle.literal_text(pts[k]) for k in keys] == [t[3] for t in terms], (seed, text)
+        assert macros["Halo"] == halo and macros["Dist"] == d and macros["Range"] == part["high"] - part["low"] + 1, (seed, text)
+        mine = st.terms()
+        assert [list(t[:3]) for t in mine] == [t[:3] for t in terms], (seed, text)
+        assert st.term_texts() == [t[3] for t in terms], (seed, text)
+        assert [t[3] for t in mine] == [float(t[3]) for t in terms], (seed, text)
+        a = st.analyze(dist, mf)
+        assert (a["halo"], a["dist"], a["range"]) == (macros["Halo"], macros["Dist"], macros["Range"]), (seed, text)
+        checked += 1
+    assert checked >= 60, checked
