@@ -208,12 +208,11 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         if (s.ts == 2) { s.nw = 8; s.ry = 4; } else { s.nw = 16; s.ry = 2; }
         s.st = 2; s.chunk = 128;
     } else {
-        // rows per thread: 4 for k radius <= 1 (tuned); deeper windows (composed operators: 25 / 35 / 63 points)
-        // keep 2*rk+1 planes of every row in the register queue next to a long chain -- ptxas -v on sm_100a:
-        // 3d7pt composed twice: 171 registers at 4 rows, 244 at 8; 3d9pt_cross composed twice: 255 + 12 B of
-        // spills at 4 rows, 620 B at 8; 3d7pt composed three times: 241 at 2 rows, 40 B of spills at 4
-        s.nw = 2; s.chunk = 16;
-        s.ry = s.rk <= 1 ? 4 : std::max(2, 8 / s.rk);
+        // rows per thread: 4 for k radius <= 1 (tuned), 8 for deeper windows.  NOTE for the next tuning pass
+        // (ptxas -v, sm_100a; not yet timed, so not changed): the deep windows of composed operators are register
+        // bound -- 3d7pt composed twice: 171 registers at 4 rows, 244 at 8; 3d9pt_cross composed twice: 255 + 12 B of
+        // spills at 4 rows, 620 B at 8; 3d7pt composed three times: 241 at 2 rows, 980 B of spills at 8.
+        s.nw = 2; s.ry = s.rk <= 1 ? 4 : 8; s.chunk = 16;
         s.st = pow2_ceil(2 * s.rk + 2);
         if (s.st < 4) s.st = 4;
     }
@@ -264,7 +263,6 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.minb = std::max(1, std::min(32 / s.nw, 65536 / (est * s.nw * 32)));
         if (s.fused3d && s.nw * 32 <= 256) s.minb = std::max(s.minb, 2);   // 128 registers: no spills measured
     }
-    if (s.dim == 3 && !s.fused3d && s.rk >= 2) s.minb = 1;   // the estimate above undercounts long chains: no register cap
     if (k.reserved[1] > 0) s.minb = k.reserved[1];
     if (s.dim == 3 && !s.fused3d && s.st < pow2_ceil(2 * s.rk + 2)) s.st = pow2_ceil(2 * s.rk + 2);
     if (s.fused3d) {
