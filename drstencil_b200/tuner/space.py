@@ -36,6 +36,10 @@ class Config:
     rows_3d: int = 0
     dtype: str = "f64"
     fuse: str = "temporal"
+    # experimental: warps of a CTA along x / y that share one input ring (single-step 3D sweep)
+    share_x: int = 1
+    share_y: int = 1
+    dim: int = 2        # selects the name grammar (the reference has one per dimensionality)
 
     def knobs(self) -> Knobs:
         k = Knobs(step=self.step, sn=self.sn, bx=self.bx, by=self.by, streaming=int(self.streaming),
@@ -57,30 +61,44 @@ class Config:
             k.set("min_blocks", self.min_blocks)
         if self.rows_3d:
             k.set("rows_3d", self.rows_3d)
+        if self.share_x * self.share_y > 1:
+            k.set("share_x", self.share_x)
+            k.set("share_y", self.share_y)
         return k
 
 
 def cfg_to_string(c: Config) -> str:
-    """The reference's result-file name grammar (tuning.py:72-86):
-    fu{step}d{dist}bx{bx}[y{by}]sn{sn}u{unroll}(bmx|cmx){m}[(bmy|cmy){m}]mf{t}[p], followed by the
+    """The reference's result-file name grammars (2D: benchmarks/2d5pt_star/tuning.py:72-86,
+    fu{step}d{dist}bx{bx}(sn{sn}u{unroll} | y{by})(bmx|cmx){m}[(bmy|cmy){m}]mf{t}[p]; 3D:
+    benchmarks/3d7pt_star/tuning.py:57-72, fu{step}d{dist}bx{bx}y{by}sn{sn}u{unroll}(bmx|cmx){m}(bmy|cmy){m}mf{t}[p]), followed by the
     engine-only axes when they differ from the defaults: st{stages} mb{min_blocks} ry{rows} and the
     dtype/fuse tags."""
-    if c.streaming:
-        s = "fu%dd%dbx%dsn%du%d" % (c.step, c.dist, c.bx, c.sn, c.s_unroll)
-    else:
-        s = "fu%dd%dbx%dy%d" % (c.step, c.dist, c.bx, c.by)
-    s += ("bmx" if c.block_merge_x else "cmx") + str(c.mx)
-    if not c.streaming:
+    if c.dim == 3:      # benchmarks/3d7pt_star/tuning.py:57-72: block shape, sn and unroll are always part of the name
+        s = "fu%dd%dbx%dy%dsn%du%d" % (c.step, c.dist, c.bx, c.by, c.sn, c.s_unroll)
+        s += ("bmx" if c.block_merge_x else "cmx") + str(c.mx)
         s += ("bmy" if c.block_merge_y else "cmy") + str(c.my)
-    s += "mf%d" % c.merge_forward
-    if c.prefetch and c.streaming:
-        s += "p"
+        s += "mf%d" % c.merge_forward
+        if c.prefetch:
+            s += "p"
+    else:
+        if c.streaming:
+            s = "fu%dd%dbx%dsn%du%d" % (c.step, c.dist, c.bx, c.sn, c.s_unroll)
+        else:
+            s = "fu%dd%dbx%dy%d" % (c.step, c.dist, c.bx, c.by)
+        s += ("bmx" if c.block_merge_x else "cmx") + str(c.mx)
+        if not c.streaming:
+            s += ("bmy" if c.block_merge_y else "cmy") + str(c.my)
+        s += "mf%d" % c.merge_forward
+        if c.prefetch and c.streaming:
+            s += "p"
     if c.stages != 4:
         s += "st%d" % c.stages
     if c.min_blocks:
         s += "mb%d" % c.min_blocks
     if c.rows_3d:
         s += "ry%d" % c.rows_3d
+    if c.share_x * c.share_y > 1:
+        s += "sx%dsy%d" % (c.share_x, c.share_y)
     if c.dtype != "f64":
         s += c.dtype
     if c.fuse != "temporal":
@@ -91,7 +109,9 @@ def cfg_to_string(c: Config) -> str:
 def cfg_to_command_line(c: Config) -> str:
     """Arguments for the `drstencil` CLI that reproduce this configuration (tuning.py:50-69)."""
     cmd = " --step %d --dist %d --bx %d" % (c.step, c.dist, c.bx)
-    if c.streaming:
+    if c.dim == 3:
+        cmd += " --by %d --sn %d --stream-unroll %d" % (c.by, c.sn, c.s_unroll)
+    elif c.streaming:
         cmd += " --streaming --sn %d --stream-unroll %d" % (c.sn, c.s_unroll)
     else:
         cmd += " --by %d" % c.by
@@ -106,6 +126,8 @@ def cfg_to_command_line(c: Config) -> str:
         cmd += " --min-blocks %d" % c.min_blocks
     if c.rows_3d:
         cmd += " --rows-3d %d" % c.rows_3d
+    if c.share_x * c.share_y > 1:
+        cmd += " --share-x %d --share-y %d" % (c.share_x, c.share_y)
     if c.dtype != "f64":
         cmd += " --dtype " + c.dtype
     if c.fuse != "temporal":
@@ -147,6 +169,14 @@ def filter_config(c: Config, dim: int, radius: int, esize: int = 8) -> bool:
         if c.stages < 2 * radius + 2:
             return False
         smem = warps * c.stages * (stage + 8)
+        if c.share_x * c.share_y > 1:                       # one ring per CTA (drs_sweep3d_cta.cuh)
+            if c.share_x * c.share_y != warps or c.step != 1 and c.fuse == "temporal":
+                return False
+            wb = c.share_x * 32 * vec + 2 * ((radius + vec - 1) // vec * vec)
+            if wb > 256:
+                return False
+            stage = (wb * (c.share_y * ry + 2 * radius) * esize + 127) // 128 * 128
+            smem = c.stages * (stage + 16)
         live = (2 * radius + 1) * ry * vec * (esize // 4)
     if smem > 227 * 1024:
         return False
@@ -157,12 +187,15 @@ def filter_config(c: Config, dim: int, radius: int, esize: int = 8) -> bool:
     ctas = min(32, 227 * 1024 // max(smem, 1), 65536 // (regs * warps * 32))
     if c.min_blocks and c.min_blocks > ctas:
         return False
-    in_flight = ctas * warps * (c.stages - 1 if dim == 2 else c.stages - 2 * radius) * stage
+    rings = 1 if c.share_x * c.share_y > 1 else warps
+    in_flight = ctas * rings * (c.stages - 1 if dim == 2 else c.stages - 2 * radius) * stage
     return ctas >= 1 and in_flight >= 24 * 1024
 
 
-def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse: str = "temporal") -> List[Config]:
-    """Cartesian product of the axes (reference: tuning.py:124-139), filtered."""
+def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse: str = "temporal",
+                 experimental: bool = False) -> List[Config]:
+    """Cartesian product of the axes (reference: tuning.py:124-139), filtered.  `experimental` adds, for 3D
+    single-step sweeps, six rows per thread, longer chunks and the CTA-shared input ring (share_x x share_y)."""
     esize = 8 if dtype == "f64" else 4
     out = []
     if dim == 2:
@@ -176,7 +209,15 @@ def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse:
         for (bx, by), sn, my, stages in itertools.product(
                 ((32, 1), (32, 2), (32, 4)), (8, 16, 32, 64), (1, 2), (4, 8)):
             c = Config(step=step, bx=bx, by=by, streaming=False, sn=sn, block_merge_y=True, my=my, rows_3d=4 * my,
-                       stages=stages, dtype=dtype, fuse=fuse)
+                       stages=stages, dtype=dtype, fuse=fuse, dim=3)
             if filter_config(c, 3, radius * (step if fuse == "algebraic" or dim == 3 else 1), esize):
                 out.append(c)
+        if experimental and step == 1:
+            for (sx, sy), sn, ry, stages in itertools.product(
+                    ((1, 1), (2, 1), (1, 2), (2, 2), (3, 2), (2, 4)), (32, 64, 128), (4, 6, 8), (4, 8)):
+                warps = sx * sy if sx * sy > 1 else 4
+                c = Config(step=1, bx=32, by=warps, streaming=False, sn=sn, block_merge_y=True, my=1, rows_3d=ry,
+                           stages=stages, dtype=dtype, fuse=fuse, share_x=sx, share_y=sy, dim=3)
+                if filter_config(c, 3, radius, esize) and c not in out:
+                    out.append(c)
     return out

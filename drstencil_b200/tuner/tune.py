@@ -49,14 +49,14 @@ def time_config(st, cfg: Config, sweeps=6, warm=2):
 
 
 def tune(stc, is3d=None, step=1, dtype="f64", fuse="temporal", size=None, budget_s=120.0, top=3, use_ncu=False,
-         peak_gbs=6553.6, log=print, resume_from=None):
+         peak_gbs=6553.6, log=print, resume_from=None, experimental=False):
     """`resume_from`: a previous result file for the same problem -- configurations already timed
     there are not run again (the reference's tuner always restarts from scratch)."""
     st = Stencil.from_file(stc, is3d)
     if size:
         st.set_size(size)
     radius = max(max(abs(t[0]), abs(t[1]), abs(t[2])) for t in st.terms())
-    space = search_space(st.dim, radius, step, dtype, fuse)
+    space = search_space(st.dim, radius, step, dtype, fuse, experimental=experimental)
     log("search space: %d configurations after the resource-model filter" % len(space))
     shape = st.shape
     esize = 4 if dtype == "f32" else 8
@@ -140,9 +140,11 @@ def main():
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--out", default="tuning_result.json")
     ap.add_argument("--resume", action="store_true", help="skip configurations already present in --out")
+    ap.add_argument("--experimental", action="store_true",
+                    help="3D single step: also search six rows per thread, longer chunks and the CTA-shared input ring")
     a = ap.parse_args()
     res = tune(a.stc, a.is3d or None, a.step, a.dtype, a.fuse, a.size, a.budget_s, a.top, a.ncu,
-               resume_from=a.out if a.resume else None)
+               resume_from=a.out if a.resume else None, experimental=a.experimental)
     json.dump(res, open(a.out, "w"), indent=1)
     for w in res["winners"]:
         print("WINNER %s  %.4f ms  %.0f GB/s (%.1f%% of %.0f)  drstencil%s" %

@@ -16,6 +16,19 @@ def test_config_name_grammar_matches_reference():
     # non-streaming: fu..d..bx..y..(bmx|cmx)m(bmy|cmy)m mf
     c = Config(step=1, dist=1, bx=32, by=8, streaming=False, block_merge_x=True, mx=2, block_merge_y=False, my=4)
     assert cfg_to_string(c) == "fu1d1bx32y8bmx2cmy4mf5"
+    # 3D (benchmarks/3d7pt_star/tuning.py:57-72): block shape, sn and unroll always named -- two configurations that
+    # differ only in sn must not share a name (result files and --resume are keyed on it)
+    c = Config(step=1, bx=32, by=2, streaming=False, sn=64, s_unroll=4, block_merge_y=True, my=1, rows_3d=6, dim=3)
+    assert cfg_to_string(c) == "fu1d0bx32y2sn64u4bmx1bmy1mf5ry6"
+    assert cfg_to_command_line(c) == (" --step 1 --dist 0 --bx 32 --by 2 --sn 64 --stream-unroll 4 --block-merge-y 1"
+                                      " --block-merge-x 1 --merge-forward 5 --rows-3d 6")
+    from drstencil_b200.tuner.space import search_space
+    for experimental in (False, True):
+        names = [cfg_to_string(x) for x in search_space(3, 1, experimental=experimental)]
+        assert len(names) == len(set(names))
+    shared = [x for x in search_space(3, 1, experimental=True) if x.share_x * x.share_y > 1]
+    assert shared and cfg_to_string(shared[0]).endswith("sx%dsy%d" % (shared[0].share_x, shared[0].share_y))
+    assert " --share-x " in cfg_to_command_line(shared[0])
     # engine axes are appended only when they differ from the defaults
     c = Config(step=4, bx=64, sn=256, mx=2, stages=8, min_blocks=4, dtype="f32", fuse="algebraic")
     assert cfg_to_string(c) == "fu4d0bx64sn256u4bmx2mf5st8mb4f32alg"
