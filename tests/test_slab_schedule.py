@@ -185,3 +185,31 @@ def test_faces_and_directions(built):
         inits = [s[5] for s in ups if s[5]]
         assert sum(bool(f & INIT_LO) for f in inits) == (1 if r > 0 else 0)
         assert sum(bool(f & INIT_UP) for f in inits) == (1 if r + 1 < len(ranks) else 0)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_engine_chosen_blocks_at_the_c5_size(built, world):
+    """c5 (1536^3 fp64) over 2 / 4 / 8 ranks with the engine's own block size: every rank gets the same number
+    of blocks (the lockstep at the faces relies on it), thin blocks at both ends, 100 signalled levels per face."""
+    import drstencil_b200 as drs
+    from drstencil_b200.presets import PRESETS
+    from drstencil_b200.slab import SlabGeometry
+    path, kn = PRESETS["c5"]
+    shapes = []
+    for rank in range(world):
+        geom = SlabGeometry(1536, world, rank, 1)
+        st = drs.Stencil.from_file(path).set_size((geom.local_planes, 1536, 1536))
+        plan = drs.Plan(st, kn)
+        plan.set_slab(1536, geom.lo, geom.hi)
+        steps = plan.slab_schedule(100, up_skew=rank % 2 == 1)
+        assert steps, (world, rank)
+        ups = [s for s in steps if s[0] == UPLOAD]
+        sizes = [s[4] - s[3] for s in ups]
+        assert sum(sizes) == geom.hi - geom.lo and min(sizes) >= 2
+        assert sizes[0] < max(sizes) and sizes[-1] < max(sizes)          # thin first and last block
+        shapes.append(len(ups))
+        sweeps = [s for s in steps if s[0] == SWEEP]
+        for sig, has in ((SIG_LO, rank > 0), (SIG_UP, rank + 1 < world)):
+            assert sorted(s[2] for s in sweeps if s[5] & sig) == (list(range(1, 101)) if has else [])
+        assert len(sweeps) <= 100 * len(ups)
+    assert len(set(shapes)) == 1, shapes
