@@ -66,6 +66,15 @@ def lib():
     if not os.path.exists(_LIBPATH):
         raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(or drstencil_b200.build())" % _LIBPATH)
+    # libdrstencil.so dlopen()s "libnvrtc.so.12"; if torch is imported later (or earlier) in the same process
+    # that name resolves to the copy torch ships (12.8 here) or to the toolkit's (12.9) depending on the ORDER of
+    # the imports, and the two compilers do not produce the same cubins (the cache key carries the version).
+    # Importing torch first pins one answer for build(), tests, bench and tools alike -- the one every GPU
+    # measurement of this repo was taken with.
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     L = ctypes.CDLL(_LIBPATH)
     vp, i32, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
     P = ctypes.POINTER

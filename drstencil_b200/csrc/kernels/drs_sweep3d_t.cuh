@@ -40,8 +40,9 @@
 //   2  + their column halo by warp shuffle
 //   3  + only the edge rows of a completed plane are published (nobody else reads the rest)
 //   4  + level 1: own vectors loaded once (128-bit), column halo shuffled as well
-// Depth >= 4: the partial sums alone fill the 128-register budget of a 16-warp CTA and levels 1..4 spill
-// (ptxas: 44 bytes); there everything is read back from shared memory as before (no spills).
+// Depth >= 4: the partial sums alone fill the 128-register budget of a 16-warp CTA and the register-resident
+// variant spills more than the read-back one (ptxas 12.9: 44 vs 0 bytes, 12.8: 16 vs 8): everything is read
+// back from shared memory there, as before.
 #ifndef DRS_T3_OWNREG
 #if DRS_TS >= 4
 #define DRS_T3_OWNREG 0
