@@ -106,7 +106,9 @@ def lib():
         "drs_plan_set_graph": (i32, [vp, i32]),
         "drs_plan_host_schedule": (i32, [vp, i32, P(ll), i32]),
         "drs_plan_slab_schedule": (i32, [vp, i32, i32, P(ll), i32]),
-        "drs_run_host_slab": (i32, [vp, vp, i32, i32, vp, vp, vp, ll, P(ctypes.c_float)]),
+        "drs_run_host_slab": (i32, [vp, vp, i32, i32, P(ctypes.c_float)]),
+        "drs_plan_set_flags": (i32, [vp, vp, vp, vp]),
+        "drs_run_slab": (i32, [vp, i32, vp, P(i32)]),
         "drs_check_error": (i32, [vp, vp, vp, P(ctypes.c_double)]),
         "drs_plan_sync_check": (i32, [vp, vp]),
         "drs_plan_launch_count": (ll, [vp]),
@@ -125,6 +127,7 @@ def lib():
         "drs_last_error": (ctypes.c_char_p, []),
         "drs_version": (ctypes.c_char_p, []),
         "drs_device_count": (i32, []),
+        "drs_set_device": (i32, [i32]),
         "drs_set_cache_dir": (None, [ctypes.c_char_p]),
     }
     for name, (res, args) in sig.items():
@@ -451,12 +454,20 @@ class Plan:
         _check(lib().drs_plan_slab_schedule(self._h, iterations, int(up_skew), buf, n))
         return [tuple(buf[6 * i:6 * i + 6]) for i in range(n)]
 
-    def run_host_slab(self, h_own, iterations: int, up_skew: bool, my_flags: int, lower_flag: int, upper_flag: int,
-                      flag_base: int) -> float:
-        """EXPERIMENTAL: this rank's share of a slab-decomposed host-buffer run (see drstencil.h); device ms."""
+    def set_flags(self, my_flags: int, lower_flag: int, upper_flag: int) -> None:
+        _check(lib().drs_plan_set_flags(self._h, my_flags, lower_flag or None, upper_flag or None))
+
+    def run_slab(self, iterations: int, stream=None) -> int:
+        """This rank's share of the emitted host loop on a slab-decomposed grid: one launch per sweep, the
+        halo exchange and the step flags fused into the sweep kernel (drs_run_slab)."""
+        n = ctypes.c_int()
+        _check(lib().drs_run_slab(self._h, iterations, _stream(stream), ctypes.byref(n)))
+        return n.value
+
+    def run_host_slab(self, h_own, iterations: int, up_skew: bool) -> float:
+        """This rank's share of a slab-decomposed host-buffer run (see drstencil.h); device ms."""
         ms = ctypes.c_float()
-        _check(lib().drs_run_host_slab(self._h, _ptr(h_own), iterations, int(up_skew), my_flags, lower_flag or None,
-                                       upper_flag or None, flag_base, ctypes.byref(ms)))
+        _check(lib().drs_run_host_slab(self._h, _ptr(h_own), iterations, int(up_skew), ctypes.byref(ms)))
         return ms.value
 
     def set_host_block(self, units: int) -> None:

@@ -55,6 +55,7 @@ struct Driver {
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;   // optional
 };
 
 Driver& driver() {
@@ -86,6 +87,13 @@ Driver& driver() {
         ok &= get("cuLaunchKernel", (void**)&d.LaunchKernel);
         ok &= get("cuTensorMapEncodeTiled", (void**)&d.TensorMapEncodeTiled);
         ok &= get("cuGetErrorString", (void**)&d.GetErrorString);
+        {
+            cudaDriverEntryPointQueryResult q;
+            void* fp = nullptr;
+            if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fp, cudaEnableDefault, &q) == cudaSuccess && fp)
+                d.StreamWriteValue64 = (decltype(d.StreamWriteValue64))fp;
+            else cudaGetLastError();
+        }
         d.ok = ok;
     });
     return d;
@@ -227,6 +235,16 @@ struct DevParams {
     void* peer_hi;
     long long push_lo0, push_lo1, peer_lo_shift;
     long long push_hi0, push_hi1, peer_hi_shift;
+    // in-kernel slab protocol (drs_run_slab)
+    const long long* my_flags;
+    long long* lower_flag;
+    long long* upper_flag;
+    const long long* seq_base;
+    unsigned int* face_cnt;
+    long long face_lo_end, face_hi_begin;
+    int seq_off;
+    int face_lo_chunks, face_hi_chunks;
+    unsigned int face_lo_units, face_hi_units;
 };
 
 }  // namespace
@@ -246,7 +264,7 @@ struct drs_plan {
     bool loaded = false;
     int device = -1;
     CUmodule mod = nullptr;
-    CUfunction f_sweep = nullptr, f_gold = nullptr, f_check = nullptr, f_signal = nullptr, f_wait = nullptr;
+    CUfunction f_sweep = nullptr, f_slab = nullptr, f_gold = nullptr, f_check = nullptr, f_signal = nullptr, f_wait = nullptr;
     int regs = 0, spill = 0;
     int* d_fault = nullptr;
     double* d_res = nullptr;
@@ -269,6 +287,14 @@ struct drs_plan {
     void* lower_bases[2] = {nullptr, nullptr};
     void* upper_bases[2] = {nullptr, nullptr};
     long long lower_lo = 0, upper_lo = 0;
+    // in-kernel step flags of drs_run_slab (drs_plan_set_flags): caller-owned flag words, plan-owned
+    // sequence base + face counters; slab_seq = sweeps run so far (flag values are monotone)
+    const void* my_flags = nullptr;
+    void* lower_flag = nullptr;
+    void* upper_flag = nullptr;
+    void* d_sync = nullptr;               // { long long seq_base; unsigned face_cnt[2]; }
+    long long slab_seq = 0;
+    std::map<int, RunGraph> slab_graphs;  // launch sequence of drs_run_slab per sweep count
 
     long long local_slow() const { return spec.dim == 3 ? st.L : st.M; }
 };
@@ -276,7 +302,14 @@ struct drs_plan {
 namespace {
 
 int ensure_loaded(drs_plan* p) {
-    if (p->loaded) return DRS_OK;
+    if (p->loaded) {
+        // the module, tensor maps and scratch memory belong to the device that was current at first use
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != p->device)
+            return fail(DRS_E_ARG, "plan is bound to CUDA device " + std::to_string(p->device) + " but device " +
+                                       std::to_string(cur) + " is current");
+        return DRS_OK;
+    }
     Driver& d = driver();
     if (!d.ok) return fail(DRS_E_NOGPU, "drstencil needs a CUDA device (no CPU fallback): " + d.why);
     cudaGetDevice(&p->device);
@@ -295,6 +328,11 @@ int ensure_loaded(drs_plan* p) {
         const int smem = p->spec.smem_bytes();
         r = d.FuncSetAttribute(p->f_sweep, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
         if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(r));
+        if (p->spec.dim == 3) {     // the entry point with the in-kernel slab protocol (drs_run_slab)
+            r = d.ModuleGetFunction(&p->f_slab, p->mod, ("drslab_" + nm).c_str());
+            if (r == CUDA_SUCCESS) r = d.FuncSetAttribute(p->f_slab, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+            if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(drslab_): " + cu_err(r));
+        }
         d.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->f_sweep);
         d.FuncGetAttribute(&p->spill, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, p->f_sweep);
     }
@@ -353,7 +391,9 @@ struct SlowRange { long long lo, hi; };   // output range along the slow axis, l
 
 // ring = frozen ring width of this launch (spec.halo, or the sub-step's share of it);
 // sub  = restrict the launch to these slow-axis outputs (time-skewed blocks of drs_run_host)
-void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int ring = -1, const SlowRange* sub = nullptr) {
+// seq_off >= 0: this launch is sweep number seq_off of a drs_run_slab call and handles its own step flags
+void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int ring = -1, const SlowRange* sub = nullptr,
+                 int seq_off = -1) {
     const drs::KernelSpec& s = p->spec;
     std::memset(&q, 0, sizeof q);
     q.in = in; q.out = out;
@@ -392,6 +432,33 @@ void fill_params(const drs_plan* p, const void* in, void* out, DevParams& q, int
     }
     q.chunk = s.chunk;
     q.fault = p->d_fault;
+    if (seq_off >= 0 && p->slab && p->my_flags && p->d_sync && s.dim == 3 && !sub && (q.peer_lo || q.peer_hi)) {
+        q.my_flags = (const long long*)p->my_flags;
+        q.lower_flag = q.peer_lo ? (long long*)p->lower_flag : nullptr;
+        q.upper_flag = q.peer_hi ? (long long*)p->upper_flag : nullptr;
+        q.seq_base = (const long long*)p->d_sync;
+        q.face_cnt = (unsigned int*)((char*)p->d_sync + sizeof(long long));
+        q.seq_off = seq_off;
+        // a chunk [za, zb) belongs to a face when it reads that neighbour's ghost planes or produces planes
+        // that are pushed to it; its input reaches Halo planes beyond its outputs on both sides
+        const long long ghost = s.halo, local = p->local_slow();
+        q.face_lo_end = 2 * ghost;
+        q.face_hi_begin = local - 2 * ghost;
+        const long long units_per_chunk = s.share3d ? (long long)s.nw * ((q.nxs + s.sx - 1) / s.sx) * ((q.nys + s.sy - 1) / s.sy)
+                                                    : (long long)q.nxs * q.nys;
+        int nlo = 0, nhi = 0;
+        for (long long zc = 0; zc < q.nzs; ++zc) {
+            const long long za = q.slow_lo + zc * s.chunk, zb = std::min(za + s.chunk, q.slow_hi);
+            if (q.lower_flag && za < q.face_lo_end) ++nlo;
+            if (q.upper_flag && zb > q.face_hi_begin) ++nhi;
+        }
+        // the kernel lists the lower-face chunks first, then the upper-face ones; a chunk that touches both
+        // faces (thin slabs) is counted on both and keeps its place in the prefix
+        q.face_lo_chunks = nlo;
+        q.face_hi_chunks = std::min<long long>(nhi, q.nzs - nlo);
+        q.face_lo_units = (unsigned int)(nlo * units_per_chunk);
+        q.face_hi_units = (unsigned int)(nhi * units_per_chunk);
+    }
 }
 
 int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
@@ -406,7 +473,8 @@ int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     return DRS_OK;
 }
 
-int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub = nullptr);
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub = nullptr,
+               int seq_off = -1);
 
 int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     if (in == out) return fail(DRS_E_ARG, "d_in and d_out must differ");
@@ -429,18 +497,20 @@ int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     return DRS_OK;
 }
 
-int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub) {
+int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub, int seq_off) {
     CUtensorMap* tm = nullptr;
     int rc = tensor_map_for(p, in, &tm);
     if (rc != DRS_OK) return rc;
+    // 128-bit stores: a misaligned destination would be a sticky device fault, not an error code
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
     DevParams q;
-    fill_params(p, in, out, q, ring, sub);
+    fill_params(p, in, out, q, ring, sub, seq_off);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;
     if (tiles <= 0) return DRS_OK;
     const long long ctas = p->spec.ctas(q.nxs, q.nys, q.nzs);
     if (ctas > 0x7fffffffLL) return fail(DRS_E_ARG, "grid too large");
     void* args[] = {tm, &q};
-    CUresult r = driver().LaunchKernel(p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
+    CUresult r = driver().LaunchKernel(q.my_flags && p->f_slab ? p->f_slab : p->f_sweep, (unsigned)ctas, 1, 1, (unsigned)(p->spec.nw * 32), 1, 1,
                                        (unsigned)p->spec.smem_bytes(), (CUstream)stream, args, nullptr);
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch dr_: " + cu_err(r));
     p->launches++;
@@ -596,6 +666,8 @@ void drs_plan_destroy(drs_plan* p) {
         cudaFree(p->d_res);
         for (void* b : p->h_dev) if (b) cudaFree(b);
         for (void* b : p->scratch) if (b) cudaFree(b);
+        if (p->d_sync) cudaFree(p->d_sync);
+        for (auto& g : p->slab_graphs) cudaGraphExecDestroy(g.second.exec);
         for (cudaStream_t st : {p->hs_up, p->hs_run, p->hs_dn, p->cap_stream}) if (st) cudaStreamDestroy(st);
         for (auto& g : p->graphs) cudaGraphExecDestroy(g.second.exec);
         if (p->mod) driver().ModuleUnload(p->mod);
@@ -652,6 +724,8 @@ int drs_gold_sweep(drs_plan* p, const void* d_in, void* d_out, void* stream) {
 static void drop_graphs(drs_plan* p) {
     for (auto& g : p->graphs) cudaGraphExecDestroy(g.second.exec);
     p->graphs.clear();
+    for (auto& g : p->slab_graphs) cudaGraphExecDestroy(g.second.exec);
+    p->slab_graphs.clear();
 }
 
 // The launch sequence of drs_run as an instantiated CUDA graph: built once per (A, B, sweep count) by
@@ -967,6 +1041,10 @@ int drs_plan_set_peers(drs_plan* p, void* const my_bases[2], void* const lower_b
     if (!p || !my_bases) return fail(DRS_E_ARG, "null argument");
     if (!p->slab) return fail(DRS_E_ARG, "call drs_plan_set_slab first");
     if (p->spec.dim != 3 || !p->spec.tma_ok) return fail(DRS_E_ARG, "fused halo push is implemented for the 3D TMA sweep");
+    for (int b = 0; b < 2; ++b)
+        for (const void* q : {(const void*)my_bases[b], lower_bases ? (const void*)lower_bases[b] : nullptr,
+                              upper_bases ? (const void*)upper_bases[b] : nullptr})
+            if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return fail(DRS_E_ARG, "slab array bases must be 16-byte aligned");
     for (int b = 0; b < 2; ++b) {
         p->my_bases[b] = my_bases[b];
         p->lower_bases[b] = lower_bases ? lower_bases[b] : nullptr;
@@ -999,6 +1077,98 @@ int drs_wait_flags(drs_plan* p, const void* my_flags, int wait_lower, int wait_u
     return DRS_OK;
 }
 
+int drs_plan_set_flags(drs_plan* p, const void* my_flags, void* lower_flag, void* upper_flag) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    if (!p->slab || !p->my_bases[0] || !p->my_bases[1]) return fail(DRS_E_ARG, "call drs_plan_set_slab and drs_plan_set_peers first");
+    if (!my_flags) return fail(DRS_E_ARG, "my_flags is null");
+    for (const void* q : {my_flags, (const void*)lower_flag, (const void*)upper_flag})
+        if ((reinterpret_cast<uintptr_t>(q) & 7) != 0) return fail(DRS_E_ARG, "flag words must be 8-byte aligned");
+    p->my_flags = my_flags; p->lower_flag = lower_flag; p->upper_flag = upper_flag;
+    drop_graphs(p);
+    return DRS_OK;
+}
+
+// One rank's share of the emitted host loop on a slab-decomposed grid.  One launch per sweep: the sweep
+// kernel waits for / signals its neighbours itself (Params::my_flags ...), the launches are replayed as a
+// CUDA graph, and the only thing that changes between calls -- the flag value of the call's first sweep --
+// lives in device memory and is written in stream order before the replay.
+int drs_run_slab(drs_plan* p, int iterations, void* stream_, int* sweeps) {
+    if (!p) return fail(DRS_E_ARG, "null plan");
+    if (!p->slab || !p->my_bases[0] || !p->my_bases[1]) return fail(DRS_E_ARG, "call drs_plan_set_slab and drs_plan_set_peers first");
+    const bool alone = !p->lower_bases[0] && !p->upper_bases[0];
+    if (!alone && !p->my_flags) return fail(DRS_E_ARG, "call drs_plan_set_flags first");
+    int rc = ensure_loaded(p);
+    if (rc != DRS_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!p->d_sync) {
+        if (cudaMalloc(&p->d_sync, 16) != cudaSuccess) return fail(DRS_E_CUDA, "cudaMalloc(slab sync words)");
+        cudaMemset(p->d_sync, 0, 16);
+    }
+    int n = 0;
+    for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
+    if (sweeps) *sweeps = n;
+    if (n == 0) return DRS_OK;
+    // flag value of this call's sweep 0, in stream order (no kernel)
+    const long long base = p->slab_seq;
+    if (driver().StreamWriteValue64) {
+        CUresult r = driver().StreamWriteValue64((CUstream)stream, (CUdeviceptr)p->d_sync, (cuuint64_t)base, 0);
+        if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuStreamWriteValue64: " + cu_err(r));
+    } else if (cudaMemcpyAsync(p->d_sync, &base, sizeof base, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+        return fail(DRS_E_CUDA, "slab sequence base upload failed");      // pageable source: staged before return
+    }
+    void* a = p->my_bases[0];
+    void* b = p->my_bases[1];
+    auto enqueue = [&](cudaStream_t st) -> int {
+        int r = DRS_OK;
+        for (int s = 0; s < n && r == DRS_OK; ++s)
+            r = (s & 1) ? launch_one(p, b, a, st, -1, nullptr, s) : launch_one(p, a, b, st, -1, nullptr, s);
+        return r;
+    };
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+    cudaGetLastError();
+    bool done = false;
+    if (p->use_graph && !capturing) {
+        auto it = p->slab_graphs.find(n);
+        if (it == p->slab_graphs.end()) {
+            CUtensorMap* tm = nullptr;
+            if ((rc = tensor_map_for(p, a, &tm)) != DRS_OK || (rc = tensor_map_for(p, b, &tm)) != DRS_OK) return rc;
+            if (!p->cap_stream && cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError(); p->use_graph = false;
+            } else if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError(); p->use_graph = false;
+            } else {
+                const long long l0 = p->launches;
+                rc = enqueue(p->cap_stream);
+                cudaGraph_t g = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &g);
+                const int kernels = (int)(p->launches - l0);
+                p->launches = l0;
+                cudaGraphExec_t exec = nullptr;
+                if (rc != DRS_OK || ce != cudaSuccess || !g || cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) {
+                    if (g) cudaGraphDestroy(g);
+                    cudaGetLastError(); p->use_graph = false;
+                    if (rc != DRS_OK) return rc;
+                } else {
+                    cudaGraphDestroy(g);
+                    if (p->slab_graphs.size() >= 8) {
+                        for (auto& x : p->slab_graphs) cudaGraphExecDestroy(x.second.exec);
+                        p->slab_graphs.clear();
+                    }
+                    it = p->slab_graphs.emplace(n, drs_plan::RunGraph{exec, kernels}).first;
+                }
+            }
+        }
+        if (p->use_graph && it != p->slab_graphs.end()) {
+            if (cudaGraphLaunch(it->second.exec, stream) == cudaSuccess) { p->launches += it->second.kernels; done = true; }
+            else { cudaGetLastError(); p->use_graph = false; }
+        }
+    }
+    if (!done && (rc = enqueue(stream)) != DRS_OK) return rc;
+    p->slab_seq += n;
+    return DRS_OK;
+}
+
 // EXPERIMENTAL executor of drs_plan_slab_schedule (written against the CPU-verified planner; not yet run on
 // GPUs -- nothing in the package or the bench calls it).  One rank's share of a slab-decomposed host-buffer
 // run: h_own holds the rank's own planes; uploads, sweeps and downloads run on three streams chained by
@@ -1006,12 +1176,16 @@ int drs_wait_flags(drs_plan* p, const void* my_flags, int wait_lower, int wait_u
 // upload that brings a face's level-0 planes is followed by a peer copy of them into the neighbour's ghosts.
 // Flags are monotone: this call uses the values flag_base + 1 ... flag_base + sweeps + 1; the caller separates
 // calls by a barrier and advances flag_base by at least sweeps + 2.
-int drs_run_host_slab(drs_plan* p, void* h_own, int iterations, int up_skew, const void* my_flags, void* lower_flag,
-                      void* upper_flag, long long flag_base, float* device_ms) {
-    if (!p || !h_own || !my_flags) return fail(DRS_E_ARG, "null argument");
+int drs_run_host_slab(drs_plan* p, void* h_own, int iterations, int up_skew, float* device_ms) {
+    if (!p || !h_own) return fail(DRS_E_ARG, "null argument");
     if (!p->slab || !p->my_bases[0] || !p->my_bases[1]) return fail(DRS_E_ARG, "call drs_plan_set_slab and drs_plan_set_peers first");
+    if (!p->my_flags) return fail(DRS_E_ARG, "call drs_plan_set_flags first");
     int rc = ensure_loaded(p);
     if (rc != DRS_OK) return rc;
+    const void* my_flags = p->my_flags;
+    void* lower_flag = p->lower_flag;
+    void* upper_flag = p->upper_flag;
+    const long long flag_base = p->slab_seq;
     int n = 0;
     for (int t = 0; t < iterations; t += 2 * p->spec.step) n += 2;
     const std::vector<drs::SlabStep> steps = slab_steps(p, n, up_skew != 0);
@@ -1101,6 +1275,7 @@ int drs_run_host_slab(drs_plan* p, void* h_own, int iterations, int up_skew, con
     const cudaError_t ce = cudaGetLastError();
     if (rc == DRS_OK && rc2 == DRS_OK && ce != cudaSuccess)
         return fail(DRS_E_CUDA, std::string("streamed slab run: ") + cudaGetErrorString(ce));
+    if (rc == DRS_OK && rc2 == DRS_OK) p->slab_seq = flag_base + n + 1;    // the largest flag value this call wrote
     return rc != DRS_OK ? rc : rc2;
 }
 
@@ -1160,6 +1335,14 @@ int drs_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+int drs_set_device(int ordinal) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail(DRS_E_NOGPU, "drstencil needs a CUDA device (no CPU fallback)"); }
+    if (ordinal < 0 || ordinal >= n) return fail(DRS_E_ARG, "no CUDA device " + std::to_string(ordinal));
+    cudaError_t e = cudaSetDevice(ordinal);
+    if (e != cudaSuccess) return fail(DRS_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return DRS_OK;
 }
 void drs_set_cache_dir(const char* dir) { g_cache_dir = dir ? dir : ""; }
 

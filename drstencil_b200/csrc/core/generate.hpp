@@ -446,6 +446,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_DIM " << s.dim << "\n";
     o << "#define DRS_T " << (s.dtype == DRS_F64 ? "double" : "float") << "\n";
     o << "#define DRS_NAME dr_" << s.name << "\n";
+    o << "#define DRS_SLAB_NAME drslab_" << s.name << "\n";
     o << "#define DRS_GOLD_NAME gold_" << s.name << "\n";
     o << "#define DRS_CHECK_NAME check_" << s.name << "\n";
     o << "#define DRS_SIGNAL_NAME signal_" << s.name << "\n";

@@ -51,6 +51,8 @@ inline HostSchedule plan_host_schedule(long long slow, long long H, long long S,
         at += (slow - at - thin > S) ? S : ((slow - at > 2 * thin) ? slow - at - thin : slow - at);
     }
     hs.edge.push_back(slow);
+    // every block must be at least 2*H thick (see above): a thinner remainder joins its predecessor
+    while (hs.edge.size() > 2 && hs.edge.back() - hs.edge[hs.edge.size() - 2] < 2 * H) hs.edge.erase(hs.edge.end() - 2);
     const int B = hs.blocks();
     auto cut = [&](int b, int s) -> long long {   // first output plane of block b at sweep s
         if (b <= 0) return H;
@@ -70,9 +72,9 @@ inline HostSchedule plan_host_schedule(long long slow, long long H, long long S,
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same block order for ONE RANK of a slab-decomposed run (planner only: the executor that would
-// drive it with the slab flags is not written yet; tests/test_slab_schedule.py runs the step lists
-// of all ranks against each other on the CPU, with random interleavings, ghost planes and flags).
+// The same block order for ONE RANK of a slab-decomposed run (executor: drs_run_host_slab;
+// tests/test_slab_schedule.py runs the step lists of all ranks against each other on the CPU, with
+// random interleavings, ghost planes and flags).
 //
 // Local plane indices: the rank's array holds `local` planes, of which [own_lo, own_hi) are its own
 // (host slab, uploaded / downloaded) and [out_lo, out_hi) are swept (out_lo > own_lo only where the
@@ -133,6 +135,7 @@ inline std::vector<SlabStep> plan_slab_schedule(SlabSide g, long long H, long lo
         at += (left - thin > S) ? S : ((left > 2 * thin) ? left - thin : left);
     }
     edge.push_back(g.own_hi);
+    while (edge.size() > 2 && edge.back() - edge[edge.size() - 2] < 2 * H) edge.erase(edge.end() - 2);
     const int B = (int)edge.size() - 1;
     auto cut = [&](int b, int s) -> long long {
         if (b <= 0) return g.out_lo;

@@ -43,6 +43,24 @@ struct Params {
     real* peer_hi;
     drs_i64 push_lo0, push_lo1, peer_lo_shift;
     drs_i64 push_hi0, push_hi1, peer_hi_shift;
+    // in-kernel slab protocol (drs_run_slab; all null / zero otherwise): the step flags of a slab run are
+    // handled by the sweep itself.  A work unit (a warp's tile, or a CTA's) whose chunk reads ghost planes
+    // or pushes into a neighbour's waits until that neighbour's slot of `my_flags` holds >= seq (the
+    // neighbour's face units of the previous sweep are done: its pushes have landed here and it no longer
+    // reads the ghost planes this sweep overwrites); when the last unit of a face has finished, seq + 1 is
+    // released into the neighbour's slot.  Face chunks are scheduled first, so a sweep signals early and
+    // its successor practically never waits.  seq = *seq_base + seq_off (seq_base is device memory, so a
+    // captured launch sequence can be replayed with a new base).
+    const drs_i64* my_flags;       // [0] written by the lower neighbour, [1] by the upper one
+    drs_i64* lower_flag;           // lower neighbour's slot 1 / upper neighbour's slot 0 (peer mapped), or null
+    drs_i64* upper_flag;
+    const drs_i64* seq_base;
+    unsigned int* face_cnt;        // [0] lower face, [1] upper face: units finished so far (self-resetting)
+    drs_i64 face_lo_end;           // a chunk [za, zb) touches the lower face iff za < face_lo_end
+    drs_i64 face_hi_begin;         //                     ... the upper face iff zb > face_hi_begin
+    int seq_off;
+    int face_lo_chunks, face_hi_chunks;   // how many chunks those are (a prefix / a suffix of the chunk list)
+    unsigned int face_lo_units, face_hi_units;   // work units per face = arrivals that complete it
 };
 
 __device__ __forceinline__ drs_u32 smem_u32(const void* p) {
@@ -92,8 +110,70 @@ __device__ __forceinline__ bool mbar_wait(drs_u64* bar, drs_u32 parity, int* fau
             if (mbar_try_wait(bar, parity)) return true;
         if (global_ns() - t0 > 1000000000ull || (fault && *(volatile int*)fault)) break;
     }
-    if (fault) atomicExch(fault, 1);
+    if (fault) atomicCAS(fault, 0, 1);
     return false;
+}
+
+// ---- in-kernel slab protocol (see Params) ----------------------------------------------------
+// Chunk order of a slab launch: the chunks of the lower face, then those of the upper face, then the
+// interior -- a sweep's boundary planes are produced (and pushed, and signalled) first.
+__device__ __forceinline__ int slab_chunk_order(const Params& p, int i) {
+    if (p.my_flags == nullptr) return i;
+    if (i < p.face_lo_chunks) return i;
+    if (i < p.face_lo_chunks + p.face_hi_chunks) return p.nzs - p.face_hi_chunks + (i - p.face_lo_chunks);
+    return i - p.face_hi_chunks;
+}
+__device__ __forceinline__ bool slab_touches_lo(const Params& p, drs_i64 za) {
+    return p.my_flags != nullptr && p.face_lo_units != 0 && za < p.face_lo_end;
+}
+__device__ __forceinline__ bool slab_touches_hi(const Params& p, drs_i64 zb) {
+    return p.my_flags != nullptr && p.face_hi_units != 0 && zb > p.face_hi_begin;
+}
+// bit 0 / bit 1: the chunk with index zc (after slab_chunk_order) touches the lower / upper face.  Cheap and
+// uniform: recomputed where it is needed instead of being kept live across the plane loop.
+__device__ __forceinline__ int slab_face(const Params& p, int zc) {
+    if (p.my_flags == nullptr) return 0;
+    const drs_i64 za = p.slow_lo + (drs_i64)zc * p.chunk;
+    const drs_i64 zb = (za + p.chunk < p.slow_hi) ? za + p.chunk : p.slow_hi;
+    return (slab_touches_lo(p, za) ? 1 : 0) | (slab_touches_hi(p, zb) ? 2 : 0);
+}
+// One thread of the unit, before the unit's first TMA request.  5 s watchdog (fault code 2).
+__device__ __forceinline__ bool slab_wait(const Params& p, bool lo, bool hi) {
+    const drs_i64 want = *p.seq_base + p.seq_off;
+    const drs_u64 t0 = global_ns();
+    for (int slot = 0; slot < 2; ++slot) {
+        if (!(slot == 0 ? lo : hi)) continue;
+        for (;;) {
+            drs_i64 v;
+            asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p.my_flags + slot) : "memory");
+            if (v >= want) break;
+            if (global_ns() - t0 > 5000000000ull || (p.fault && *(volatile int*)p.fault)) {
+                if (p.fault) atomicCAS(p.fault, 0, 2);
+                return false;
+            }
+            __nanosleep(100);
+        }
+    }
+    // the ghost planes were written through the generic proxy (peer stores); the TMA unit reads them
+    // through the async proxy
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    return true;
+}
+// One thread of the unit, after every thread of the unit has fenced its stores (__threadfence_system)
+// and the unit has synchronised.
+__device__ __forceinline__ void slab_arrive(const Params& p, bool lo, bool hi) {
+    const drs_i64 next = *p.seq_base + p.seq_off + 1;
+    __threadfence_system();
+    if (lo && atomicAdd(&p.face_cnt[0], 1u) + 1u == p.face_lo_units) {
+        p.face_cnt[0] = 0u;                      // the next launch starts after this one has drained
+        __threadfence_system();
+        if (p.lower_flag) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.lower_flag), "l"(next) : "memory");
+    }
+    if (hi && atomicAdd(&p.face_cnt[1], 1u) + 1u == p.face_hi_units) {
+        p.face_cnt[1] = 0u;
+        __threadfence_system();
+        if (p.upper_flag) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p.upper_flag), "l"(next) : "memory");
+    }
 }
 
 // TMA tile loads: global -> shared, completion counted in bytes on an mbarrier.

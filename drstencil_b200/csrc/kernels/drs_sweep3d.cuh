@@ -167,13 +167,15 @@ __device__ __forceinline__ bool phases(real (&q)[K2][RY][kVec], const Stream& st
     }
 }
 
+// SLAB: the entry point of drs_run_slab (in-kernel step flags, face chunks first)
+template <bool SLAB>
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const drs_i64 tile = (drs_i64)blockIdx.x * NW + warp;
     const drs_i64 per_chunk = (drs_i64)p.nxs * p.nys;
     if (tile >= per_chunk * p.nzs) return;
-    const int zc = (int)(tile / per_chunk);
+    const int zc = SLAB ? slab_chunk_order(p, (int)(tile / per_chunk)) : (int)(tile / per_chunk);
     const int rem = (int)(tile % per_chunk);
     const int ys = rem / p.nxs;
     const int xs = rem % p.nxs;
@@ -228,6 +230,16 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.lo0 = p.push_lo0; t.lo1 = p.push_lo1; t.lo_shift = p.peer_lo_shift;
     t.hi0 = p.push_hi0; t.hi1 = p.push_hi1; t.hi_shift = p.peer_hi_shift;
 
+    // slab runs (drs_run_slab): a tile next to a neighbour's slab waits for that neighbour's previous sweep
+    if constexpr (SLAB) {
+        const int face = slab_face(p, zc);       // warp-uniform
+        if (face) {
+            int ok = 1;
+            if (lane == 0) ok = slab_wait(p, face & 1, face & 2) ? 1 : 0;
+            if (!__shfl_sync(0xffffffffu, ok, 0)) return;
+        }
+    }
+
     if (lane == 0) {
         for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
     }
@@ -244,6 +256,14 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     for (int n0 = 0; n0 < st.NIT; n0 += K2) {
         if (!phases<0>(q, st, t, n0)) return;
     }
+    if constexpr (SLAB) {
+        const int face = slab_face(p, slab_chunk_order(p, (int)(((drs_i64)blockIdx.x * NW + warp) / ((drs_i64)p.nxs * p.nys))));
+        if (face) {
+            __threadfence_system();  // this lane's stores (own planes and pushed ghost planes) before the signal
+            __syncwarp();
+            if (lane == 0) slab_arrive(p, face & 1, face & 2);
+        }
+    }
 }
 
 }  // namespace s3d
@@ -251,5 +271,9 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
 extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
 DRS_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
-    drs::s3d::sweep(tmap, p);
+    drs::s3d::sweep<false>(tmap, p);
+}
+extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
+DRS_SLAB_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
+    drs::s3d::sweep<true>(tmap, p);
 }

@@ -165,6 +165,8 @@ __device__ __forceinline__ bool phases(real (&q)[K2][RY][kVec], const Stream& st
     }
 }
 
+// SLAB: the entry point of drs_run_slab (in-kernel step flags, face chunks first)
+template <bool SLAB>
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const int nxc = (p.nxs + SX - 1) / SX, nyc = (p.nys + SY - 1) / SY;   // CTA tiles per plane
     const drs_i64 per_chunk = (drs_i64)nxc * nyc;
     const drs_i64 cta = blockIdx.x;
-    const int zc = (int)(cta / per_chunk);
+    const int zc = SLAB ? slab_chunk_order(p, (int)(cta / per_chunk)) : (int)(cta / per_chunk);
     const int rem = (int)(cta % per_chunk);
     const int cys = rem / nxc, cxs = rem % nxc;
 
@@ -234,8 +236,17 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.lo0 = p.push_lo0; t.lo1 = p.push_lo1; t.lo_shift = p.peer_lo_shift;
     t.hi0 = p.push_hi0; t.hi1 = p.push_hi1; t.hi_shift = p.peer_hi_shift;
 
+    // slab runs (drs_run_slab): only the producer waits for the neighbour's previous sweep -- everything the
+    // other warps do (including their pushes) depends on planes it requests afterwards.  If the wait fails
+    // nothing is requested and every warp leaves through the fault check of its first mbarrier wait.
     if (threadIdx.x == 0) {
-        for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
+        bool go = true;
+        if constexpr (SLAB) {
+            const int face = slab_face(p, zc);
+            go = !face || slab_wait(p, face & 1, face & 2);
+        }
+        if (go)
+            for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
     }
 
     real q[K2][RY][kVec];
@@ -250,6 +261,15 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     for (int n0 = 0; n0 < st.NIT; n0 += K2) {
         if (!phases<0>(q, st, t, n0)) return;
     }
+    if constexpr (SLAB) {            // the unit of the slab protocol is the warp: NW arrivals per CTA
+        const int nxc2 = (p.nxs + SX - 1) / SX, nyc2 = (p.nys + SY - 1) / SY;
+        const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((drs_i64)nxc2 * nyc2))));
+        if (face) {
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) slab_arrive(p, face & 1, face & 2);
+        }
+    }
 }
 
 }  // namespace s3c
@@ -257,5 +277,9 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
 extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
 DRS_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
-    drs::s3c::sweep(tmap, p);
+    drs::s3c::sweep<false>(tmap, p);
+}
+extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
+DRS_SLAB_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
+    drs::s3c::sweep<true>(tmap, p);
 }

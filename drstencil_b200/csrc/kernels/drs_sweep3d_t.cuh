@@ -253,6 +253,9 @@ __device__ __forceinline__ bool phases(real (&pw)[TS][K2][RY][kVec], const Ctx& 
     }
 }
 
+// SLAB: the entry point of drs_run_slab (in-kernel step flags, face chunks first); the plain entry point carries
+// none of it (its register allocation sits at the 128-register cap)
+template <bool SLAB>
 __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Ctx c;
@@ -266,7 +269,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
     const drs_i64 tile = blockIdx.x;
     const drs_i64 per_chunk = (drs_i64)p.nxs * p.nys;
-    const int zc = (int)(tile / per_chunk);
+    const int zc = SLAB ? slab_chunk_order(p, (int)(tile / per_chunk)) : (int)(tile / per_chunk);
     const int rem = (int)(tile % per_chunk);
     const int cy = rem / p.nxs, cx = rem % p.nxs;
 
@@ -316,8 +319,16 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.lo0 = p.push_lo0; c.lo1 = p.push_lo1; c.lo_shift = p.peer_lo_shift;
     c.hi0 = p.push_hi0; c.hi1 = p.push_hi1; c.hi_shift = p.peer_hi_shift;
 
+    // slab runs (drs_run_slab): the thread that requests the planes waits for the neighbour's previous sweep
+    // (on failure nothing is requested and the CTA leaves through the fault check of its first wait)
     if (threadIdx.x == 0) {
-        for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
+        bool go = true;
+        if constexpr (SLAB) {
+            const int face = slab_face(p, zc);
+            go = !face || slab_wait(p, face & 1, face & 2);
+        }
+        if (go)
+            for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
     }
 
     real pw[TS][K2][RY][kVec];
@@ -332,7 +343,15 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
 #pragma unroll 1
     for (int n0 = 0; n0 < c.NIT; n0 += K2) {
-        if (!phases<0>(pw, c, n0)) break;
+        if (!phases<0>(pw, c, n0)) return;       // watchdog: every warp of the CTA fails the same wait
+    }
+    if constexpr (SLAB) {                        // the unit of the slab protocol is the CTA
+        const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((drs_i64)p.nxs * p.nys))));
+        if (face) {                              // CTA-uniform
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) slab_arrive(p, face & 1, face & 2);
+        }
     }
 }
 
@@ -341,5 +360,9 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
 extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
 DRS_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
-    drs::s3t::sweep(tmap, p);
+    drs::s3t::sweep<false>(tmap, p);
+}
+extern "C" __global__ void __launch_bounds__(DRS_NW * 32, DRS_MINB)
+DRS_SLAB_NAME(const __grid_constant__ drs::TensorMap tmap, const __grid_constant__ drs::Params p) {
+    drs::s3t::sweep<true>(tmap, p);
 }

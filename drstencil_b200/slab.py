@@ -6,13 +6,16 @@ config c5.  Semantics are those of ONE global grid swept by the reference's sche
 Halo-wide ring stays frozen, every rank owns planes [lo, hi) and keeps `ghost` = Halo copies of
 its neighbours' boundary planes on each side.
 
-Two exchange paths:
-  "p2p"   the sweep kernel itself stores its boundary planes a second time, straight into the
-          neighbour's ghost planes over NVLink (buffers mapped with CUDA IPC, drs_plan_set_peers);
-          ranks then only trade a step flag (drs_signal_peers / drs_wait_flags) -- no collective,
-          no extra copy kernel, and the transfer overlaps the rest of the sweep;
-  "nccl"  plain torch.distributed isend/irecv of the boundary planes after each sweep (NCCL on GPUs,
-          gloo on CPU -- the path the CPU tests drive with a stand-in sweep).
+Exchange paths (`halo=`):
+  "p2p"        drs_run_slab: ONE launch per sweep.  The sweep kernel stores its boundary planes a second
+               time, straight into the neighbour's ghost planes over NVLink (buffers mapped with CUDA IPC),
+               and handles the step flags itself: tiles next to a neighbour wait (ld.acquire.sys) for that
+               neighbour's previous sweep, the last boundary tile of a face releases the next flag value;
+               boundary tiles run first.  No collective, no extra kernel, the whole schedule is one CUDA graph.
+  "p2p-flags"  the same push, but the flags as separate one-thread kernels around every sweep (three launches
+               per sweep, driven from Python) -- round 1's protocol, kept for A/B measurements.
+  "nccl"       plain torch.distributed isend/irecv of the boundary planes after each sweep (NCCL on GPUs,
+               gloo on CPU -- the path the CPU tests drive with a stand-in sweep).
 """
 from __future__ import annotations
 
@@ -187,7 +190,8 @@ class GpuSlab:
         for b in self.bufs:
             b.zero_()
         self._peer_ptrs: List[int] = []
-        if halo == "p2p" and world > 1:
+        self._flags = None
+        if halo in ("p2p", "p2p-flags") and world > 1:
             self._flags = _DevArray((2,), "<i8", 8)
             self._flags.tensor().zero_()
             mine = [_ipc_export(r.ptr) for r in self._raw] + [_ipc_export(self._flags.ptr)]
@@ -207,14 +211,20 @@ class GpuSlab:
             # a rank writes slot 1 of its lower neighbour's flags and slot 0 of its upper neighbour's
             self._lower_flag = lower[2] + 8 if lower else 0
             self._upper_flag = upper[2] if upper else 0
+            self.plan.set_flags(self._flags.ptr, self._lower_flag, self._upper_flag)
+            torch.cuda.synchronize()
             dist.barrier(group=group)
+        elif halo == "p2p":
+            self.plan.set_peers([r.ptr for r in self._raw], [0, 0], [0, 0], 0, 0)
+        # flag values are monotone over the life of the object (sweeps run so far): never reset
+        self._seq = 0
         self.runner = SlabRunner(self.geom, self.bufs, self._sweep, self._after, self._before)
 
     # -- schedule hooks --
     def _before(self, s: int) -> None:
-        if self.mode == "p2p" and self.world > 1 and s > 0:
+        if self.mode == "p2p-flags" and self.world > 1:
             g = self.geom
-            self.plan.wait_flags(self._flags.ptr, g.lower is not None, g.upper is not None, s)
+            self.plan.wait_flags(self._flags.ptr, g.lower is not None, g.upper is not None, self._seq)
 
     def _sweep(self, src, dst) -> None:
         self.plan.sweep(src, dst)
@@ -222,59 +232,53 @@ class GpuSlab:
     def _after(self, dst, s: int) -> None:
         if self.world == 1:
             return
-        if self.mode == "p2p":
-            self.plan.signal_peers(self._lower_flag, self._upper_flag, s + 1)
+        if self.mode == "p2p-flags":
+            self._seq += 1
+            self.plan.signal_peers(self._lower_flag, self._upper_flag, self._seq)
         else:
             halo_exchange(dst, self.geom, self.group)
 
     # -- data --
     def fill(self, plane_fn: Callable) -> None:
         """A[local plane] = plane_fn(global plane index) for every in-grid plane this rank holds
-        (owned and ghost); B = 0.  Resets the schedule."""
+        (owned and ghost); B = 0.  Restarts the schedule at sweep(A, B).  Collective: every rank calls it."""
+        import torch
         import torch.distributed as dist
         g = self.geom
+        if self.world > 1:
+            # nobody may still be pushing into these arrays: all ranks drain their streams first
+            self.plan.sync_check()
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
         self.bufs[0].zero_()
         self.bufs[1].zero_()
         for zl in range(g.local_planes):
             zg = g.origin + zl
             if 0 <= zg < g.g_slow:
                 self.bufs[0][zl].copy_(plane_fn(zg))
-        if self.mode == "p2p" and self.world > 1:
-            self.plan.sync_check()
-            self._flags.tensor().zero_()
-            import torch
+        if self.world > 1:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
         self.runner.sweeps_done = 0
 
     def run(self, timesteps: int) -> int:
+        if self.mode == "p2p":
+            return self.plan.run_slab(timesteps)
         return self.runner.run(timesteps, self.step)
 
     def run_host(self, h_own, timesteps: int) -> float:
-        """EXPERIMENTAL (not yet validated on GPUs): the reference schedule on this rank's HOST slab `h_own`
-        (own planes only, pinned), uploads / sweeps / downloads overlapped by time-skewed blocks, faces in
-        lockstep with the neighbours (drs_run_host_slab).  Needs the "p2p" halo mode and a GpuSlab of its
-        own: run() and run_host() number the step flags differently and must not be mixed on one object.
-        Returns device ms."""
+        """The reference schedule on this rank's HOST slab `h_own` (own planes only, pinned), uploads / sweeps /
+        downloads overlapped by time-skewed blocks, faces in lockstep with the neighbours (drs_run_host_slab).
+        Needs the "p2p" halo mode.  Collective (contains the barrier that separates calls).  Returns device ms.
+        The device copy of B must hold zeros in its frozen ring (true after construction or fill())."""
         import torch
         import torch.distributed as dist
         if self.mode != "p2p" or self.world < 2:
             raise ValueError("run_host needs the p2p halo mode and at least two ranks (one GPU: Plan.run_host)")
-        if self.runner.sweeps_done:
-            raise ValueError("this GpuSlab has been used with run(); create a separate one for run_host()")
-        n = 0
-        t = 0
-        while t < timesteps:
-            n += 2
-            t += 2 * self.step
         self.plan.sync_check()
         torch.cuda.synchronize()
         dist.barrier(group=self.group)               # nobody still reads ghosts of the previous call
-        base = getattr(self, "_flag_base", 0)
-        ms = self.plan.run_host_slab(h_own, timesteps, self.rank % 2 == 1, self._flags.ptr, self._lower_flag,
-                                     self._upper_flag, base)
-        self._flag_base = base + n + 2
-        return ms
+        return self.plan.run_host_slab(h_own, timesteps, self.rank % 2 == 1)
 
     def owned(self, which: int = 0):
         """The rank's owned planes of buffer `which` (0 = A, where the result lands)."""
@@ -282,152 +286,22 @@ class GpuSlab:
         return self.bufs[which][g.ghost:g.ghost + (g.hi - g.lo)]
 
     def close(self) -> None:
+        """Collective: unmaps the neighbours' arrays and frees this rank's."""
         from . import lib
         import torch
         torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)           # no neighbour still pushes into / reads from these arrays
         for p in self._peer_ptrs:
             lib().drs_ipc_close(p)
         self._peer_ptrs = []
-
-
-def bench_slab(args, rank, world, workload, peak_info, timed_start=None, timed_end=None):
-    """bench.py's N > 1 leg: c5 (3d7pt_star fp64 1536^3) over `world` GPUs, strong scaling.
-    `timed_start` / `timed_end` bracket the timed region (clock sampling)."""
-    import time
-    import torch
-    import torch.distributed as dist
-    from . import sweep_count
-    from .presets import PRESETS
-    preset, timesteps, desc = workload
-    path, kn = PRESETS[preset]
-    if getattr(args, "depth", 1) > 1:
-        from . import Knobs
-        kn = Knobs(step=args.depth)
-        desc += " [temporal depth %d]" % args.depth
-    slab = GpuSlab(path, kn, rank, world, halo=args.halo)
-    L, M, N = slab.global_shape
-    g = torch.Generator(device="cuda")
-    dtype = slab.dtype
-
-    def plane(zg):
-        g.manual_seed(1234 + zg)
-        return torch.rand((M, N), dtype=dtype, device="cuda", generator=g) * 1e-100
-
-    slab.fill(plane)
-    info = slab.plan.info
-    for _ in range(max(3, args.warmup)):
-        slab.run(timesteps)
-    slab.plan.sync_check()
-    dist.barrier()
-    torch.cuda.synchronize()
-    l0 = slab.plan.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if timed_start:
-        timed_start()
-    e0.record()
-    for _ in range(args.steps):
-        slab.run(timesteps)
-    e1.record()
-    slab.plan.sync_check()
-    clocks = timed_end() if timed_end else None
-    secs = e0.elapsed_time(e1) * 1e-3
-    t = torch.tensor([secs], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs = float(t)
-    launches = slab.plan.launch_count - l0
-    H = info.halo
-    sweeps = sweep_count(timesteps, kn.step)
-    upd = (L - 2 * H) * (M - 2 * H) * (N - 2 * H) * sweeps * kn.step
-    value = upd * args.steps / secs / 1e9
-    peak, peak_src = peak_info
-    esize = 8 if slab.dtype == torch.float64 else 4
-    geom = slab.geom
-    local_bytes = (geom.hi - geom.lo) * M * N * 2 * esize        # algorithmic bytes of this rank's launch
-    sweep_launches = sweeps * args.steps
-    ach = local_bytes / (secs / sweep_launches) / 1e9
-    halo_bytes = 2 * geom.ghost * M * N * esize                  # pushed per sweep by an interior rank
-    line = {
-        "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if esize == 8 else "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (preset, desc), "grid": [L, M, N], "timesteps_per_step": timesteps,
-                   "decomposition": "k-slabs, %d planes per GPU + %d ghost planes per side" % (geom.hi - geom.lo, geom.ghost),
-                   "halo_exchange": "fused NVLink peer stores from the sweep kernel + step flags" if args.halo == "p2p"
-                   else "NCCL isend/irecv after each sweep",
-                   "halo_bytes_per_sweep_per_gpu": halo_bytes, "kernel": info.kernel_name,
-                   "l2": "inputs larger than L2 (%.1f GiB per rank per sweep)" % (local_bytes / 2 ** 30)},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": info.kernel_name, "per": "GPU (rank 0's slab)",
-                     "algorithmic_bytes_per_launch": local_bytes, "launch_ms": secs / sweep_launches * 1e3},
-        "clocks": clocks,
-    }
-    # e2e: pinned host slab -> device, the schedule, result back (every step)
-    own = slab.owned(0)
-    h = torch.empty(own.shape, dtype=own.dtype, pin_memory=True)
-    h.fill_(0.5e-100)
-
-    def e2e_step():
-        own.copy_(h, non_blocking=True)
-        if world > 1:
-            halo_exchange(slab.bufs[0], geom, None) if args.halo == "nccl" else _p2p_refresh(slab)
-        slab.run(timesteps)
-        h.copy_(own, non_blocking=True)
-
-    e2e_steps = 2
-    e2e_step()                  # untimed warm-up: the first ghost refresh sets up the NCCL point-to-point channels
-    h.fill_(0.5e-100)
-    slab.plan.sync_check()
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    slab.plan.sync_check()
-    es = e0.elapsed_time(e1) * 1e-3
-    t = torch.tensor([es], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    es = float(t)
-    line["e2e"] = {"value": upd * e2e_steps / es / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": own.numel() * esize * world,
-                   "d2h_bytes_per_step": own.numel() * esize * world, "steps": e2e_steps, "ms_per_step": es / e2e_steps * 1e3,
-                   "api": "GpuSlab.run on pinned host slabs (one process per GPU)"}
-    slab.close()
-    for r in slab._raw:
-        r.free()
-    del slab
-    torch.cuda.empty_cache()
-    # extra evidence in the same run: the same grid with in-kernel temporal depth 2 (fused halo push of
-    # two ghost planes per side); the contract value above stays the bit-exact depth-1 sweep
-    if getattr(args, "depth", 1) == 1 and not getattr(args, "no_extras", False):
-        try:
-            from . import Knobs
-            kn2 = Knobs(step=2)
-            s2 = GpuSlab(path, kn2, rank, world, halo=args.halo)
-            s2.fill(plane)
-            s2.run(timesteps)
-            s2.plan.sync_check()
-            dist.barrier()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(3):
-                s2.run(timesteps)
-            e1.record()
-            s2.plan.sync_check()
-            t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            H2 = s2.plan.info.halo
-            upd2 = (L - 2 * H2) * (M - 2 * H2) * (N - 2 * H2) * sweep_count(timesteps, 2) * 2
-            line["temporal_fused"] = {"depth": 2, "value": upd2 * 3 / float(t) / 1e9, "unit": "GStencil/s",
-                                      "ms_per_step": float(t) / 3 * 1e3, "kernel": s2.plan.info.kernel_name,
-                                      "parity": "<= 1e-12 relative vs the composed operator (tests), bit-identical to the single-GPU run"}
-            s2.close()
-        except Exception as e:   # extra only
-            line["temporal_fused"] = {"error": str(e)[:200]}
-    return line
-
-
-def _p2p_refresh(slab: "GpuSlab") -> None:
-    """After new host data was uploaded into the owned planes, rebuild the neighbours' ghosts with
-    a plain exchange (the fused push only covers planes a sweep has just produced)."""
-    halo_exchange(slab.bufs[0], slab.geom, slab.group)
+        self.bufs = []
+        self.runner = None
+        self.plan = None
+        for r in self._raw:
+            r.free()
+        self._raw = []
+        if self._flags is not None:
+            self._flags.free()
+            self._flags = None

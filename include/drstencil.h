@@ -161,21 +161,14 @@ int drs_plan_set_host_block(drs_plan *p, long long units);
  * the slow-axis range copied / produced; per block: its upload, its sweeps, its download.  Returns the
  * number of records (pass NULL to query), 0 when the plain sequence would run. */
 int drs_plan_host_schedule(const drs_plan *p, int iterations, long long *records5, int capacity);
-/* PLANNER ONLY (no executor yet): the step list one rank of a slab-decomposed host-buffer run would execute so
- * that its copies overlap its sweeps like drs_run_host does on one GPU.  The plan must be a slab
- * (drs_plan_set_slab); up_skew = 0 for even ranks (blocks bottom-up, ranges sliding down), 1 for odd ranks (the
- * mirror image), so that the blocks meeting at a face run in lockstep.  Records of six values {kind, block, sweep,
- * lo, hi, faces}, local plane indices; faces is a bit set: 1 / 2 wait for the lower / upper neighbour's flag
- * >= sweep before the launch, 4 / 8 signal sweep + 1 to it afterwards, 16 / 32 (uploads) push the level-0 face
- * planes to it and signal 1.  Returns the number of records (NULL to query), 0 when the plain sequence applies. */
+/* The step list one rank of a slab-decomposed host-buffer run executes so that its copies overlap its sweeps
+ * like drs_run_host does on one GPU (needs no GPU).  The plan must be a slab (drs_plan_set_slab); up_skew = 0 for
+ * even ranks (blocks bottom-up, ranges sliding down), 1 for odd ranks (the mirror image), so that the blocks meeting
+ * at a face run in lockstep.  Records of six values {kind, block, sweep, lo, hi, faces}, local plane indices; faces
+ * is a bit set: 1 / 2 wait for the lower / upper neighbour's flag >= sweep before the launch, 4 / 8 signal sweep + 1
+ * to it afterwards, 16 / 32 (uploads) push the level-0 face planes to it and signal 1.  Returns the number of
+ * records (NULL to query), 0 when the plain sequence applies. */
 int drs_plan_slab_schedule(const drs_plan *p, int iterations, int up_skew, long long *records6, int capacity);
-/* EXPERIMENTAL executor of that step list (not yet validated on GPUs; nothing in the package calls it): this
- * rank's share of a slab-decomposed host-buffer run.  h_own = the rank's own planes (pinned for overlap), result
- * written back in place; the device arrays are the ones given to drs_plan_set_peers (second one zero-initialised
- * by the caller); my_flags / lower_flag / upper_flag as for drs_wait_flags / drs_signal_peers.  Flag values used:
- * flag_base + 1 ... flag_base + sweeps + 1 -- separate calls by a barrier and advance flag_base by sweeps + 2. */
-int drs_run_host_slab(drs_plan *p, void *h_own, int iterations, int up_skew, const void *my_flags, void *lower_flag,
-                      void *upper_flag, long long flag_base, float *device_ms);
 /* checkError2D / checkError3D (common.hpp:47-102) on device buffers: res[0] = max |a-b| (floored
  * at 1e-13 like the reference), res[1] = RMS, over [Halo, dim-Halo) */
 int drs_check_error(drs_plan *p, const void *d_out, const void *d_ref, double res[2]);
@@ -199,11 +192,32 @@ int drs_plan_set_slab(drs_plan *p, long long global_slow, long long lo, long lon
  * owned global planes (their `lo`). */
 int drs_plan_set_peers(drs_plan *p, void *const my_bases[2], void *const lower_bases[2],
                        void *const upper_bases[2], long long lower_lo, long long upper_lo);
-/* Cross-GPU step flags.  Each rank owns a device array of two 64-bit slots (slot 0 written by its
- * lower neighbour, slot 1 by its upper neighbour), exported with drs_ipc_export.  drs_signal_peers
- * enqueues, after the work already on `stream`, a system-scope release store of `value` into the
- * lower neighbour's slot 1 (`lower_flag` = that address) and the upper neighbour's slot 0;
- * drs_wait_flags enqueues a wait until the selected slots of `my_flags` hold >= value. */
+/* Cross-GPU step flags.  Each rank owns a device array of two 64-bit slots (slot 0 written by its lower
+ * neighbour, slot 1 by its upper neighbour), zero-initialised, allocated with drs_device_malloc and exported with
+ * drs_ipc_export.  drs_plan_set_flags hands the plan this rank's array and the two remote slots it writes:
+ * lower_flag = the lower neighbour's slot 1, upper_flag = the upper neighbour's slot 0 (NULL where there is no
+ * neighbour).  Flag values are monotone over the life of the plan (sweeps run so far), never reset. */
+int drs_plan_set_flags(drs_plan *p, const void *my_flags, void *lower_flag, void *upper_flag);
+/* This rank's share of the emitted host loop (codegen.hpp:575-589) on a slab-decomposed grid: `for (t = 0; t <
+ * iterations; t += 2*step) { sweep(A,B); sweep(B,A); }` over the arrays given to drs_plan_set_peers, ONE kernel
+ * launch per sweep, replayed as a CUDA graph.  The sweep kernel does the whole exchange itself: tiles next to a
+ * neighbour's slab wait (ld.acquire.sys) until that neighbour's boundary tiles of the previous sweep are done,
+ * boundary planes are stored a second time into the neighbour's ghost planes over NVLink, and the last boundary
+ * tile of a face releases the next flag value (st.release.sys); boundary tiles are scheduled first, so the
+ * signal leaves early and the next sweep does not wait.  Every rank must call it with the same `iterations`;
+ * after new data was written into the arrays (ghost planes included) the ranks must pass a barrier of the
+ * caller's before the next call.  Writes the number of sweeps to *sweeps. */
+int drs_run_slab(drs_plan *p, int iterations, void *stream, int *sweeps);
+/* This rank's share of a slab-decomposed HOST-buffer run (the executor of drs_plan_slab_schedule): h_own = the
+ * rank's own planes (pinned for overlap), result written back in place; uploads, sweeps and downloads overlap
+ * by time-skewed blocks, the faces run in lockstep with the neighbours through the plan's flags.  The device
+ * arrays are the ones given to drs_plan_set_peers (second one zero-initialised by the caller).  Ranks pass a
+ * barrier of the caller's between calls.  up_skew as for drs_plan_slab_schedule.  *device_ms as drs_run_host. */
+int drs_run_host_slab(drs_plan *p, void *h_own, int iterations, int up_skew, float *device_ms);
+/* The protocol's two halves as separate one-thread kernels (what drs_run_slab fuses into the sweep; used by
+ * drs_run_host_slab and kept for A/B measurements): drs_signal_peers enqueues, after the work already on
+ * `stream`, a system-scope release store of `value` into the given remote slots; drs_wait_flags enqueues a wait
+ * until the selected slots of `my_flags` hold >= value. */
 int drs_signal_peers(drs_plan *p, void *lower_flag, void *upper_flag, long long value, void *stream);
 int drs_wait_flags(drs_plan *p, const void *my_flags, int wait_lower, int wait_upper, long long value, void *stream);
 /* CUDA IPC plumbing so that one process per GPU can map a neighbour's buffer.  Buffers to be
@@ -226,6 +240,9 @@ int drs_emit_program(const drs_stencil *s, const drs_knobs *k, const char *kerne
 const char *drs_last_error(void);
 const char *drs_version(void);
 int drs_device_count(void);
+/* makes CUDA device `ordinal` current for the calling thread (one process per GPU: LOCAL_RANK); a plan is bound
+ * to the device that is current at its first sweep */
+int drs_set_device(int ordinal);
 /* pre-compiles without a GPU and stores the cubin in the on-disk cache (build step) */
 int drs_plan_warm_cache(const drs_stencil *s, const drs_knobs *k);
 void drs_set_cache_dir(const char *dir);

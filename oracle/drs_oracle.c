@@ -42,6 +42,16 @@ int drs_oracle_threads(void) {
 #endif
 }
 
+/* bench.py's CPU legs: use n threads from now on, whatever OMP_NUM_THREADS said when the library was loaded
+ * (torch.distributed.run exports OMP_NUM_THREADS=1 to every rank) */
+void drs_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* common.hpp:9-11 -- rand()/(RAND_MAX-1), one draw per element, row-major.  `reseed` != 0
  * puts glibc's generator back in its never-seeded state (srand(1)). */
 void drs_oracle_fill_rand(double *a, size_t n, int reseed) {

@@ -48,6 +48,8 @@ def lib():
         L = ctypes.CDLL(so)
         ll, i32, vp = ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p
         L.drs_oracle_threads.restype = i32
+        L.drs_oracle_set_threads.argtypes = [i32]
+        L.drs_oracle_set_threads.restype = None
         L.drs_oracle_fill_rand.argtypes = [vp, ctypes.c_size_t, i32]
         L.drs_oracle_fill_rand_f32.argtypes = [vp, ctypes.c_size_t, i32]
         L.drs_oracle_fill_lcg.argtypes = [vp, ctypes.c_size_t, ctypes.c_uint]
@@ -61,6 +63,12 @@ def lib():
         L.drs_oracle_check_error.argtypes = [i32, ll, ll, ll, i32, vp, vp, vp]
         _LIB = L
     return _LIB
+
+
+def set_threads(n: int) -> int:
+    """OpenMP threads of the sweeps from now on (bench.py: all host cores even under torchrun's OMP_NUM_THREADS=1)."""
+    lib().drs_oracle_set_threads(int(n))
+    return lib().drs_oracle_threads()
 
 
 # --------------------------------------------------------------------------------------------

@@ -32,6 +32,19 @@ def test_reference_arm_line(built):
     assert d["e2e"] == {"value": d["value"], "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_uses_every_host_core_under_torchrun_env(built):
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU legs must not inherit that
+    (round 1: the N > 1 reference arm ran on one core and inflated every N > 1 ratio ~15x)."""
+    r = _bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "c1", "--gpus", "2",
+               env={"OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"})
+    assert r.returncode == 0, r.stderr[-800:]
+    d = json.loads(r.stdout.strip())
+    cb = d["cpu_baseline"]
+    cores = len(os.sched_getaffinity(0))
+    assert cb["host_cores"] == cores and cb["cores"] == cores, cb
+    assert "warning" not in cb
+
+
 def test_reference_arm_other_ranks_stay_silent(built):
     r = _bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "c1", "--gpus", "2",
                env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})

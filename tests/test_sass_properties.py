@@ -42,9 +42,12 @@ def test_tma_mbarrier_pipeline_and_vector_stores(built, preset):
     assert _count(ops, "SYNCS.ARRIVE.TRANS64") >= 2               # mbarrier.arrive.expect_tx
     assert _count(ops, "SYNCS.PHASECHK.TRANS64.TRYWAIT") >= 2     # mbarrier.try_wait.parity
     assert _count(ops, "STG.E.128") >= 1                          # one 128-bit store per interior vector
-    # the only per-thread global loads are the volatile reads of the watchdog flag (mbar_wait)
+    # the only per-thread global loads are the volatile reads of the watchdog flag (mbar_wait) and, in the 3D
+    # kernels, the slab protocol's words (drs_common.cuh: ld.acquire.sys of the step flags, the sequence base):
+    # a handful of scalar loads outside the plane loop, never grid data
     ldg = {k: n for k, n in ops.items() if k.startswith("LDG")}
-    assert set(ldg) <= {"LDG.E.STRONG.SYS"} and sum(ldg.values()) <= 8, ldg
+    allowed = {"LDG.E.STRONG.SYS"} | ({"LDG.E.64", "LDG.E.64.STRONG.SYS"} if dim == 3 else set())
+    assert set(ldg) <= allowed and sum(ldg.values()) <= (16 if dim == 3 else 8), ldg
     assert _count(ops, "LDL") == 0 and _count(ops, "STL") == 0    # no local-memory traffic (spills)
 
 
