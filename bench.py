@@ -390,6 +390,7 @@ def parity_slab(rank, world, halo):
             try:
                 h = torch.stack([plane(z) for z in range(slab.geom.lo, slab.geom.hi)]).cpu().pin_memory()
                 slab.fill(plane)                 # B's ring back to zeros, flags untouched
+                slab.plan.set_host_block(8)      # several blocks even on this small grid
                 slab.run_host(h, timesteps)
                 hd = h.cuda()
                 r2, p2 = _rel_errors(hd, ref)

@@ -363,7 +363,15 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     // 128 B are equal), 128 B for row boxes (2D: no difference).  DRS_TMA_L2PROMO=0..3 overrides (development aid).
     CUtensorMapL2promotion promo = s.dim == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char* e = getenv("DRS_TMA_L2PROMO")) promo = (CUtensorMapL2promotion)atoi(e);
-    if (s.dim == 2) {
+    if (s.flat) {
+        // one flat 1D tensor over the whole array; a tile is fetched as one box of wb() elements per row
+        cuuint64_t dims[1] = {(cuuint64_t)p->st.L * (cuuint64_t)p->st.M * (cuuint64_t)p->st.N};
+        cuuint32_t box[1] = {(cuuint32_t)s.wb()};
+        cuuint32_t estr[1] = {1};
+        r = driver().TensorMapEncodeTiled(&m, dt, 1, const_cast<void*>(base), dims, nullptr, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (s.dim == 2) {
         cuuint64_t dims[2] = {(cuuint64_t)p->st.N, (cuuint64_t)p->st.M};
         cuuint64_t strides[1] = {(cuuint64_t)p->st.N * es};
         cuuint32_t box[2] = {(cuuint32_t)s.wb(), (cuuint32_t)s.rb};
@@ -502,7 +510,7 @@ int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int 
     int rc = tensor_map_for(p, in, &tm);
     if (rc != DRS_OK) return rc;
     // 128-bit stores: a misaligned destination would be a sticky device fault, not an error code
-    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
+    if (!p->spec.flat && (reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
     DevParams q;
     fill_params(p, in, out, q, ring, sub, seq_off);
     const long long tiles = (long long)q.nxs * q.nys * q.nzs;

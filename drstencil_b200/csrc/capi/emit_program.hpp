@@ -56,16 +56,18 @@ static double check_result(const real_t* out, const real_t* ref) {   // common.h
     return sqrt(error / ((double)(k1 - k0) * (double)(GridM - 2 * Halo) * (double)(GridN - 2 * Halo)));
 }
 )";
-    o << "static drs::Params make_params(const real_t* in, real_t* out) {\n"
+    // `ring` = frozen ring of this launch: Halo, or a sub-step's share of it when a temporal depth runs as one
+    // single-step launch per sub-step (KernelSpec::sub_launches)
+    o << "static drs::Params make_params(const real_t* in, real_t* out, int ring = Halo) {\n"
          "    drs::Params p; memset(&p, 0, sizeof p);\n"
-         "    p.in = in; p.out = out; p.L = GridL; p.M = GridM; p.N = GridN; p.halo = Halo;\n"
-         "    p.slow_lo = Halo; p.slow_hi = (DRS_DIM == 3 ? GridL : GridM) - Halo;\n";
-    o << "    const long long a0 = (Halo / " << s.vec() << ") * " << s.vec() << ";\n";
-    o << "    p.nxs = (int)(((GridN - Halo) - a0 + " << s.wu() - 1 << ") / " << s.wu() << ");\n";
+         "    p.in = in; p.out = out; p.L = GridL; p.M = GridM; p.N = GridN; p.halo = ring;\n"
+         "    p.slow_lo = ring; p.slow_hi = (DRS_DIM == 3 ? GridL : GridM) - ring;\n";
+    o << "    const long long a0 = (ring / " << s.vec() << ") * " << s.vec() << ";\n";
+    o << "    p.nxs = (int)(((GridN - ring) - a0 + " << s.wu() - 1 << ") / " << s.wu() << ");\n";
     o << "    p.chunk = " << s.chunk << ";\n";
     o << "    const long long nslow = (p.slow_hi - p.slow_lo + p.chunk - 1) / p.chunk;\n";
     if (s.dim == 2) o << "    p.nys = (int)nslow; p.nzs = 1;\n";
-    else o << "    p.nys = (int)((GridM - 2 * Halo + " << s.tile_rows_useful() - 1 << ") / " << s.tile_rows_useful() << "); p.nzs = (int)nslow;\n";
+    else o << "    p.nys = (int)((GridM - 2 * ring + " << s.tile_rows_useful() - 1 << ") / " << s.tile_rows_useful() << "); p.nzs = (int)nslow;\n";
     o << "    return p;\n}\n";
     o << R"(
 static int* g_fault = 0;
@@ -86,7 +88,11 @@ static void gold_launch(const real_t* in, real_t* out) {
              "        if (!encode) { printf(\"CUDA error : cuTensorMapEncodeTiled unavailable\\n\"); exit(-1); } }\n"
              "    CUtensorMap m;\n";
         o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
-        if (s.dim == 2) {
+        if (s.flat) {
+            o << "    cuuint64_t dims[1] = {(cuuint64_t)GridL * GridM * GridN}; cuuint64_t* strides = 0;\n";
+            o << "    cuuint32_t box[1] = {" << s.wb() << "}; cuuint32_t es[1] = {1};\n";
+            o << "    CUresult r = encode(&m, dt, 1, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+        } else if (s.dim == 2) {
             o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
             o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
             o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
@@ -96,18 +102,41 @@ static void gold_launch(const real_t* in, real_t* out) {
             o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.box_rows() << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
             o << "    CUresult r = encode(&m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
         }
-        o << "        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
+        o << "        CU_TENSOR_MAP_SWIZZLE_NONE, " << (s.dim == 3 ? "CU_TENSOR_MAP_L2_PROMOTION_L2_256B" : "CU_TENSOR_MAP_L2_PROMOTION_L2_128B")
+          << ", CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
              "    if (r != CUDA_SUCCESS) { printf(\"CUDA error : cuTensorMapEncodeTiled failed (%d)\\n\", (int)r); exit(-1); }\n"
              "    return m;\n}\n";
-        o << "static void dr_launch(const real_t* in, real_t* out) {\n"
-             "    static CUtensorMap maps[2]; static const real_t* bases[2] = {0, 0};\n"
-             "    int b = (bases[0] == in) ? 0 : (bases[1] == in) ? 1 : (bases[0] == 0 ? 0 : 1);\n"
-             "    if (bases[b] != in) { maps[b] = make_map(in); bases[b] = in; }\n"
-             "    drs::Params p = make_params(in, out); p.fault = g_fault;\n"
-             "    const long long tiles = (long long)p.nxs * p.nys * p.nzs;\n";
-        o << "    const unsigned ctas = (unsigned)((tiles + " << s.tiles_per_cta() - 1 << ") / " << s.tiles_per_cta() << ");\n";
+        o << "static void dr_launch_one(const real_t* in, real_t* out, int ring) {\n"
+             "    static CUtensorMap maps[4]; static const real_t* bases[4] = {0, 0, 0, 0}; static int used = 0;\n"
+             "    int b = 0;\n"
+             "    while (b < used && bases[b] != in) ++b;\n"
+             "    if (b == used) { b = used < 4 ? used++ : 0; maps[b] = make_map(in); bases[b] = in; }\n"
+             "    drs::Params p = make_params(in, out, ring); p.fault = g_fault;\n"
+             "    const long long tiles = (long long)p.nxs * p.nys * p.nzs;\n"
+             "    if (tiles <= 0) return;\n";
+        if (s.share3d)
+            o << "    const unsigned ctas = (unsigned)(((p.nxs + " << s.sx - 1 << ") / " << s.sx << ") * ((p.nys + " << s.sy - 1 << ") / " << s.sy << ") * p.nzs);\n";
+        else
+            o << "    const unsigned ctas = (unsigned)((tiles + " << s.tiles_per_cta() - 1 << ") / " << s.tiles_per_cta() << ");\n";
         o << "    drs::TensorMap tm; memcpy(&tm, &maps[b], sizeof tm);\n";
         o << "    DRS_NAME<<<ctas, " << s.nw * 32 << ", " << s.smem_bytes() << ">>>(tm, p);\n}\n";
+        if (s.sub_launches > 1) {
+            // one sweep = sub_launches single-step launches with frozen rings of r, 2r, ... through scratch buffers
+            // whose rings are never read (the library does the same: capi.cpp launch_sweep)
+            o << "static void dr_launch(const real_t* in, real_t* out) {\n"
+                 "    static real_t* scratch[2] = {0, 0};\n"
+                 "    const size_t nbytes = (size_t)GridL * GridM * GridN * sizeof(real_t);\n";
+            o << "    for (int i = 0; i < " << (s.sub_launches > 2 ? 2 : 1) << "; ++i)\n"
+                 "        if (!scratch[i]) { cudaMalloc(&scratch[i], nbytes); check_error(\"Failed to allocate the temporal scratch buffer.\\n\"); }\n";
+            o << "    const real_t* src = in;\n"
+                 "    for (int s = 1; s <= " << s.sub_launches << "; ++s) {\n"
+                 "        real_t* dst = s == " << s.sub_launches << " ? out : scratch[(s - 1) & 1];\n"
+                 "        dr_launch_one(src, dst, s * " << s.base_order << ");\n"
+                 "        src = dst;\n"
+                 "    }\n}\n";
+        } else {
+            o << "static void dr_launch(const real_t* in, real_t* out) { dr_launch_one(in, out, Halo); }\n";
+        }
     } else {
         o << "static void dr_launch(const real_t* in, real_t* out) { gold_launch(in, out); }\n";
     }

@@ -31,7 +31,11 @@ struct KernelSpec {
     std::vector<Term> gold;     // the composed operator, gold order
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
     int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
-    bool tma_ok = true;         // false -> rows not 16-byte multiples: naive kernel does the sweep
+    bool tma_ok = true;         // false -> the naive kernel does the sweep (operator too deep, flat array too long)
+    // row pitch not a multiple of 16 bytes: no tiled tensor map exists; the array is described as one flat 1D
+    // tensor, a tile arrives as one TMA request per row, rows sit 128 bytes apart in shared memory and stores
+    // are scalar (drs_common.cuh: DRS_FLAT)
+    bool flat = false;
     // 3D `--step n` in temporal mode: n launches of the single-step kernel with frozen rings of
     // r, 2r, ... n*r through plan-owned scratch buffers (sub-steps exactly as a fused kernel would
     // evaluate them; not yet fused in one kernel -- no HBM saving, but no 25/35-point operator either)
@@ -65,7 +69,8 @@ struct KernelSpec {
     int tile_rows() const { return fused3d ? nw * ry : ry; }
     int tile_rows_useful() const { return fused3d ? nw * ry - 2 * (ts - 1) * rj : ry; }
     int box_rows() const { return (share3d ? sy * ry : tile_rows()) + 2 * rj; }
-    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * box_rows() * esize(); }
+    int rp() const { return flat ? (wb() * esize() + 127) / 128 * 128 / esize() : wb(); }   // smem row pitch, elements
+    int stage_bytes() const { return dim == 2 ? rb * rp() * esize() : rp() * box_rows() * esize(); }
     int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
     int smem_bytes() const {
         if (fused3d) return (st + 2 * (ts - 1)) * stage_stride() + st * 8;
@@ -123,6 +128,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     comp.compose(k.step);
     s.gold = comp.terms();
     const int vec = s.vec();
+    s.flat = (st.N % vec) != 0;   // row pitch not a multiple of 16 bytes -> flat 1D tensor map (drs_common.cuh)
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
     if (temporal) {
         // The reference multiplies the operator out and prints the result with 6 significant digits
@@ -239,7 +245,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     {
         // reserved[6] bits 2-3 / 4-5: warps of a CTA along x / y that share one ring (value - 1); 0 = private rings
         const int shx = ((k.reserved[6] >> 2) & 3) + 1, shy = ((k.reserved[6] >> 4) & 3) + 1;
-        if (s.dim == 3 && !s.fused3d && s.ts == 1 && shx * shy > 1) {
+        if (s.dim == 3 && !s.fused3d && s.ts == 1 && shx * shy > 1 && !s.flat) {   // (the shared ring has no flat form)
             s.share3d = true; s.sx = shx; s.sy = shy; s.nw = shx * shy;
             if (s.wb() > 256 || s.box_rows() > 256) return "shared tile exceeds the 256-element TMA box";
         }
@@ -271,10 +277,19 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     if (s.chunk > slow_out) s.chunk = (int)slow_out;
     if (s.chunk < 1) s.chunk = 1;
+
     while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d && !s.share3d) s.nw /= 2;
     while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
-    // TMA needs 16-byte row pitch
-    s.tma_ok = (st.N % vec) == 0;
+    s.tma_ok = true;
+    if (s.flat) {
+        // a flat coordinate is a 32-bit signed element index; the surplus iterations of a tile run a few planes /
+        // rows past the end of the array
+        const long double total = (long double)(s.dim == 3 ? st.L + 4 * (2 * s.halo + 2) : 1) * (long double)(st.M + 64) * (long double)st.N;
+        if (total >= 2147483647.0L) {
+            s.tma_ok = false;
+            s.note = "row pitch is not a multiple of 16 bytes and the array has more than 2^31 elements: naive kernel used";
+        }
+    }
     if (s.smem_bytes() > 227 * 1024) {
         // e.g. a radius-3 3D operator composed three times (radius 9: a ring of 32 planes): the reference still
         // emits a program for it, so the plan falls back to the naive one-thread-per-point kernel instead of failing
@@ -457,6 +472,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
     if (s.share3d) o << "#define DRS_SX " << s.sx << "\n#define DRS_SY " << s.sy << "\n";
+    if (s.flat) o << "#define DRS_FLAT 1\n";
     // development aid: DRS_EXTRA_DEFINES="A=1;B=2" adds `#define A 1` ... to the translation unit
     // (tools/probe_shape.py experiments; part of the source, hence of the cubin cache key)
     if (const char* xd = std::getenv("DRS_EXTRA_DEFINES")) {

@@ -14,6 +14,17 @@
 #error "DRS_T (element type) must be defined by the generated translation unit"
 #endif
 
+// DRS_FLAT: the grid's row pitch is not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32), so no
+// tiled tensor map with row / plane strides exists.  The array is then described as ONE flat 1D tensor and a
+// tile arrives as one TMA request per row (a flat coordinate needs no alignment); rows are spaced 128 bytes
+// apart in shared memory (the destination of every request must be 128-byte aligned), and stores are scalar,
+// since rows start at alternating 16-byte offsets.  What the zero fill of the tiled map did at the ends of a
+// row is lost -- a box hanging over a row end reads the neighbouring row instead -- which is harmless: every
+// output whose cone leaves the grid lies in the frozen ring and is never stored.
+#ifndef DRS_FLAT
+#define DRS_FLAT 0
+#endif
+
 typedef unsigned int drs_u32;
 typedef unsigned long long drs_u64;
 typedef long long drs_i64;
@@ -24,6 +35,11 @@ typedef DRS_T real;
 constexpr int kVec = 16 / (int)sizeof(real);  // elements per 128-bit access: 2 (f64) or 4 (f32)
 
 struct __align__(64) TensorMap { drs_u64 opaque[16]; };  // CUtensorMap, encoded on the host
+
+// row pitch of a staged tile in shared memory, in elements, for a TMA box WB elements wide
+__host__ __device__ constexpr int smem_row_pitch(int wb) {
+    return DRS_FLAT ? (int)(((wb * sizeof(real) + 127) / 128 * 128) / sizeof(real)) : wb;
+}
 
 // Kernel parameters common to the 2D and 3D sweeps (sizes are runtime values: unlike the
 // reference, which bakes L/M/N in as macros, one compiled plan serves any grid size).
@@ -189,6 +205,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_1d(void* dst, const TensorMap* map, int x, drs_u64* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -213,7 +235,10 @@ __device__ __forceinline__ void lds_vec(real (&v)[kVec], const real* p) {
     }
 }
 __device__ __forceinline__ void stg_vec(real* p, const real (&v)[kVec]) {
-    if constexpr (sizeof(real) == 8) {
+    if constexpr (DRS_FLAT != 0) {          // rows start at any element: no 16-byte alignment to rely on
+#pragma unroll
+        for (int x = 0; x < kVec; ++x) p[x] = v[x];
+    } else if constexpr (sizeof(real) == 8) {
         *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     } else {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

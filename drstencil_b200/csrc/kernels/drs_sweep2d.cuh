@@ -59,8 +59,9 @@ constexpr int WT = 32 * C;          // columns a warp computes per row
 constexpr int WU = WT - 2 * HW;     // columns it stores
 constexpr int WB = WT + 2 * E0;     // TMA box width
 constexpr int ST = DRS_ST, RB = DRS_RB, NW = DRS_NW;
-constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);
-constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+constexpr int RP = smem_row_pitch(WB);   // row pitch inside a stage (== WB unless DRS_FLAT)
+constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);           // bytes the TMA unit delivers per stage
+constexpr int STAGE_STRIDE = (RB * RP * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
 // iterations between a row entering and the output that completes with it leaving
 constexpr int DEPTH = TS == 1 ? R2 : 2 * TS * RJ + TS - 1;
@@ -194,10 +195,18 @@ struct Stream {
     int x_box, yrow0;       // TMA coordinates: box column, level-0 row of iteration 0
     int NIT, NCH;           // input rows / stages this tile streams
     int lane;
+    drs_i64 N;              // row pitch of the grid (flat coordinates)
     __device__ __forceinline__ void issue(int c) const {
         const int s = c & (ST - 1);
         mbar_expect_tx(&bars[s], STAGE_BYTES);
+#if DRS_FLAT
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+            tma_load_1d(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap,
+                        (int)((drs_i64)(yrow0 + c * RB + r) * N + x_box), &bars[s]);
+#else
         tma_load_2d(wbase + s * STAGE_STRIDE, tmap, x_box, yrow0 + c * RB, &bars[s]);
+#endif
     }
 };
 
@@ -211,7 +220,7 @@ __device__ __forceinline__ bool iteration(real (&w)[NLV][R2][SW], const Stream& 
     if (rr == 0) {
         if (!mbar_wait(&st.bars[s], (drs_u32)((c / ST) & 1), st.fault)) return false;
     }
-    const real* srow = reinterpret_cast<const real*>(st.wbase + s * STAGE_STRIDE) + rr * WB;
+    const real* srow = reinterpret_cast<const real*>(st.wbase + s * STAGE_STRIDE) + rr * RP;
     row_step<PH>(w, srow, t, n);
     if (rr == RB - 1) {
         __syncwarp();
@@ -248,6 +257,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.tmap = &tmap;
     st.fault = p.fault;
     st.lane = lane;
+    st.N = p.N;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], 1);

@@ -41,8 +41,9 @@ constexpr int WB = WT + 2 * E0;       // box width
 constexpr int YB = RY + 2 * RJ;       // box height
 constexpr int ST = DRS_ST, NW = DRS_NW;
 constexpr int LA = ST - 2 * RK;       // planes requested ahead of the one being consumed
-constexpr int STAGE_BYTES = WB * YB * (int)sizeof(real);
-constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
+constexpr int RP = smem_row_pitch(WB);   // row pitch inside a staged plane (== WB unless DRS_FLAT)
+constexpr int STAGE_BYTES = WB * YB * (int)sizeof(real);           // bytes the TMA unit delivers per plane
+constexpr int STAGE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
 static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
 static_assert(LA >= 1, "ring must hold the whole k window plus at least one plane in flight");
@@ -73,10 +74,18 @@ struct Stream {
     int x_box, y_box, z0;      // TMA coordinates of iteration 0
     int NIT;
     int lane;
+    drs_i64 M, N;              // grid pitches (flat coordinates)
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
         mbar_expect_tx(&bars[s], STAGE_BYTES);
+#if DRS_FLAT
+        const drs_i64 row0 = ((drs_i64)(z0 + n) * M + y_box) * N + x_box;
+#pragma unroll
+        for (int r = 0; r < YB; ++r)
+            tma_load_1d(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(row0 + r * N), &bars[s]);
+#else
         tma_load_3d(wbase + s * STAGE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
+#endif
     }
     __device__ __forceinline__ const real* plane(int n) const {
         return reinterpret_cast<const real*>(wbase + (n & (ST - 1)) * STAGE_STRIDE);
@@ -88,15 +97,15 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
     if (!mbar_wait(&st.bars[n & (ST - 1)], (drs_u32)((n / ST) & 1), st.fault)) return false;
     // newest plane: own vectors of every tile row into the queue
     {
-        const real* pl = st.plane(n) + RJ * WB + E0 + t.lane * kVec;
+        const real* pl = st.plane(n) + RJ * RP + E0 + t.lane * kVec;
 #pragma unroll
-        for (int y = 0; y < RY; ++y) lds_vec(q[PH][y], pl + y * WB);
+        for (int y = 0; y < RY; ++y) lds_vec(q[PH][y], pl + y * RP);
     }
     if (n >= t.n_first && n < t.n_end) {
         // staged planes of the window: sp[dk + RK] -> this thread's element 0 of tile row 0
         const real* sp[K2];
 #pragma unroll
-        for (int d = 0; d < K2; ++d) sp[d] = st.plane(n - 2 * RK + d) + RJ * WB + E0 + t.lane * kVec;
+        for (int d = 0; d < K2; ++d) sp[d] = st.plane(n - 2 * RK + d) + RJ * RP + E0 + t.lane * kVec;
         const drs_i64 z = t.z_out0 + n;
         real* orow = t.out + (z * t.M + t.y_first) * t.N + t.x_first;
         const bool push_lo = t.peer_lo != nullptr && z >= t.lo0 && z < t.lo1;
@@ -115,12 +124,12 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
 #define DRS_OPERAND_(dk, dj, di)                                                               \
     (((v + (di)) >= 0 && (v + (di)) < kVec && (y + (dj)) >= 0 && (y + (dj)) < RY)              \
          ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][clampi(v + (di), 0, kVec - 1)]         \
-         : sp[(dk) + RK][(y + (dj)) * WB + v + (di)])
+         : sp[(dk) + RK][(y + (dj)) * RP + v + (di)])
 #else
 #define DRS_OPERAND_(dk, dj, di)                                                               \
     (((di) == 0 && (y + (dj)) >= 0 && (y + (dj)) < RY)                                         \
          ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][v]                                     \
-         : sp[(dk) + RK][(y + (dj)) * WB + v + (di)])
+         : sp[(dk) + RK][(y + (dj)) * RP + v + (di)])
 #endif
 #define DRS_MUL_(dk, dj, di, c) acc = rmul(DRS_OPERAND_(dk, dj, di), (real)(c));
 #define DRS_FMA_(dk, dj, di, c) acc = rfma(DRS_OPERAND_(dk, dj, di), (real)(c), acc);
@@ -186,6 +195,8 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.tmap = &tmap;
     st.fault = p.fault;
     st.lane = lane;
+    st.M = p.M;
+    st.N = p.N;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], 1);

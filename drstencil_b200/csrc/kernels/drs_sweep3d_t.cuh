@@ -62,8 +62,9 @@ constexpr int HW = (((TS - 1) * E + kVec - 1) / kVec) * kVec;   // columns lost 
 constexpr int HY = (TS - 1) * RJ;                               // rows lost per side
 constexpr int WT = 32 * kVec, WU = WT - 2 * HW, WB = WT + 2 * E0;
 constexpr int TY = NW * RY, TYU = TY - 2 * HY, YB = TY + 2 * RJ;
-constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);
-constexpr int PLANE_STRIDE = (PLANE_BYTES + 127) / 128 * 128;
+constexpr int RP = smem_row_pitch(WB);   // row pitch of every plane in shared memory (== WB unless DRS_FLAT)
+constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);           // bytes the TMA unit delivers per plane
+constexpr int PLANE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int NLV = TS - 1;                                     // intermediate levels kept in shared memory
 constexpr int DEPTH = 2 * TS * RK + TS - 1;
 static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
@@ -96,7 +97,14 @@ struct Ctx {
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
         mbar_expect_tx(&bars[s], PLANE_BYTES);
+#if DRS_FLAT
+        const drs_i64 row0 = ((drs_i64)(z0 + n) * M + y_box) * N + x_box;
+#pragma unroll 4
+        for (int r = 0; r < YB; ++r)
+            tma_load_1d(ring + s * PLANE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(row0 + r * N), &bars[s]);
+#else
         tma_load_3d(ring + s * PLANE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
+#endif
     }
 };
 
@@ -112,7 +120,7 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         } else {
             src = reinterpret_cast<const real*>(c.lv + ((s >= 2 ? s - 2 : 0) * 2 + ((n + 1) & 1)) * PLANE_STRIDE);
         }
-        const real* mine = src + (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;   // tile row 0, element 0
+        const real* mine = src + (c.warp * RY + RJ) * RP + E0 + c.lane * kVec;   // tile row 0, element 0
         // ---- scatter into the partial sums of level s ----
 #if DRS_T3_OWNREG
         // Levels >= 2: the thread's own part of the source plane is still in its registers -- the slot
@@ -139,7 +147,7 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         real u0[RY][kVec];
         if (s == 1) {
 #pragma unroll
-            for (int y = 0; y < RY; ++y) lds_vec(u0[y], mine + y * WB);
+            for (int y = 0; y < RY; ++y) lds_vec(u0[y], mine + y * RP);
 #pragma unroll
             for (int y = 0; y < RY; ++y)
 #pragma unroll
@@ -147,15 +155,15 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
                     xl[y][e] = __shfl_up_sync(0xffffffffu, u0[y][kVec - E + e], 1);
                     xr[y][e] = __shfl_down_sync(0xffffffffu, u0[y][e], 1);
                     if constexpr (HW < TS * E) {
-                        if (c.lane == 0) xl[y][e] = mine[y * WB - E + e];
-                        if (c.lane == 31) xr[y][e] = mine[y * WB + kVec + e];
+                        if (c.lane == 0) xl[y][e] = mine[y * RP - E + e];
+                        if (c.lane == 31) xr[y][e] = mine[y * RP + kVec + e];
                     }
                 }
         }
 #endif
 #define DRS_XNBR_(yy, xx) ((xx) < 0 ? xl[yy][E + (xx)] : xr[yy][(xx) - kVec])
 #else
-#define DRS_XNBR_(yy, xx) mine[(yy) * WB + (xx)]
+#define DRS_XNBR_(yy, xx) mine[(yy) * RP + (xx)]
 #endif
 #define DRS_OWN_(yy, xx) (((xx) >= 0 && (xx) < kVec) ? pw[s >= 2 ? s - 2 : 0][mod_k2(PH - 1 - RK)][clampi(yy, 0, RY - 1)][clampi(xx, 0, kVec - 1)] \
                                                      : DRS_XNBR_(clampi(yy, 0, RY - 1), xx))
@@ -163,12 +171,12 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
 #define DRS_OWN0_(yy, xx) (((xx) >= 0 && (xx) < kVec) ? u0[clampi(yy, 0, RY - 1)][clampi(xx, 0, kVec - 1)] \
                                                       : DRS_XNBR_(clampi(yy, 0, RY - 1), xx))
 #define DRS_U_(dj, di) (((y + (dj)) >= 0 && (y + (dj)) < RY) ? (s >= 2 ? DRS_OWN_(y + (dj), v + (di)) : DRS_OWN0_(y + (dj), v + (di))) \
-                                                             : mine[(y + (dj)) * WB + v + (di)])
+                                                             : mine[(y + (dj)) * RP + v + (di)])
 #else
-#define DRS_U_(dj, di) ((s >= 2 && (y + (dj)) >= 0 && (y + (dj)) < RY) ? DRS_OWN_(y + (dj), v + (di)) : mine[(y + (dj)) * WB + v + (di)])
+#define DRS_U_(dj, di) ((s >= 2 && (y + (dj)) >= 0 && (y + (dj)) < RY) ? DRS_OWN_(y + (dj), v + (di)) : mine[(y + (dj)) * RP + v + (di)])
 #endif
 #else
-#define DRS_U_(dj, di) mine[(y + (dj)) * WB + v + (di)]
+#define DRS_U_(dj, di) mine[(y + (dj)) * RP + v + (di)]
 #endif
 #pragma unroll
         for (int y = 0; y < RY; ++y) {
@@ -190,7 +198,7 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         // ---- the plane of level s completed by this iteration ----
         if (s < TS) {
             real* dst = reinterpret_cast<real*>(c.lv + ((s - 1) * 2 + (n & 1)) * PLANE_STRIDE) +
-                        (c.warp * RY + RJ) * WB + E0 + c.lane * kVec;
+                        (c.warp * RY + RJ) * RP + E0 + c.lane * kVec;
 #pragma unroll
             for (int y = 0; y < RY; ++y) {
 #if DRS_T3_OWNREG >= 3
@@ -199,8 +207,8 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
                 real o[kVec];
 #pragma unroll
                 for (int v = 0; v < kVec; ++v) o[v] = pw[s < TS ? s - 1 : 0][mod_k2(PH - RK)][y][v];
-                if constexpr (sizeof(real) == 8) *reinterpret_cast<double2*>(dst + y * WB) = make_double2(o[0], o[1]);
-                else *reinterpret_cast<float4*>(dst + y * WB) = make_float4(o[0], o[1], o[2], o[3]);
+                if constexpr (sizeof(real) == 8) *reinterpret_cast<double2*>(dst + y * RP) = make_double2(o[0], o[1]);
+                else *reinterpret_cast<float4*>(dst + y * RP) = make_float4(o[0], o[1], o[2], o[3]);
             }
         } else if (n >= c.n_first && n < c.n_end) {
             const drs_i64 z = c.z_out0 + n;

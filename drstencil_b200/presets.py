@@ -1,10 +1,14 @@
 """Named configurations: the eight stencil descriptions the reference ships
 (/root/reference/benchmarks/*/*.stc, re-typed under stc/) and the five BASELINE.json workloads.
-Knob values for the BASELINE entries are what the tuner (drstencil_b200/tuner) settled on; the
-evidence is under profiles/."""
+
+The BASELINE entries are TUNER RECORDS: each is stated as the configuration name (the reference's result-file
+grammar, tuning.py:72-86, plus the engine's axes -- tuner/space.py) of the winner of a tuner run on B200, whose
+record under profiles/r02_tune_<workload>.json carries the Nsight Compute metrics that justify it (DRAM bytes and
+GB/s, L2 and shared-memory traffic).  tests/test_tuner.py checks every entry against its record."""
 import os
 
 from . import Knobs
+from .tuner.space import cfg_from_string
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _STC = os.path.join(_ROOT, "stc")
@@ -12,6 +16,23 @@ _STC = os.path.join(_ROOT, "stc")
 
 def _p(*parts):
     return os.path.join(_STC, *parts)
+
+
+# workload -> (stc file, dimensionality, configuration name == winners[0].name of profiles/r02_tune_<workload>.json)
+TUNED = {
+    "c1": (_p("baseline", "c1_2d5pt_star.stc"), 2, "fu1d0bx64sn128u4bmx2mf5st2"),
+    "c2": (_p("baseline", "c2_2d9pt_box.stc"), 2, "fu4d0bx64sn256u4bmx2mf5st2"),
+    "c3": (_p("baseline", "c3_2d25pt_box.stc"), 2, "fu1d0bx64sn32u8bmx1mf5st2mb4f32"),
+    "c4": (_p("baseline", "c4_3d7pt_star.stc"), 3, "fu1d0bx32y2sn16u4bmx1bmy1mf5ry4"),
+    # four warps (2 x 2) sharing one input ring per CTA, eight rows per thread: 386.6 vs 376.8 GStencil/s sustained
+    # for round 1's private rings (profiles/r02_c5_shared_ring_probe.txt)
+    "c5": (_p("baseline", "c5_3d7pt_star.stc"), 3, "fu1d0bx32y4sn64u4bmx1bmy1mf5ry8sx2sy2"),
+}
+
+
+def _tuned(name):
+    path, dim, cfg = TUNED[name]
+    return (path, cfg_from_string(cfg, dim).knobs())
 
 
 # name -> (stc file, knobs)
@@ -24,13 +45,8 @@ PRESETS = {
     "2d25pt_box": (_p("2d25pt_box.stc"), Knobs()),
     "3d7pt_star": (_p("3d7pt_star.stc"), Knobs()),
     "3d9pt_cross": (_p("3d9pt_cross.stc"), Knobs()),
-    # BASELINE.json configs
-    "c1": (_p("baseline", "c1_2d5pt_star.stc"), Knobs(sn=128, warps=2, vectors=2, stages=2, rows_per_stage=4)),
-    "c2": (_p("baseline", "c2_2d9pt_box.stc"), Knobs(step=4, sn=256, vectors=2, stages=2)),
-    "c3": (_p("baseline", "c3_2d25pt_box.stc"), Knobs(dtype="f32", sn=32, warps=2, rows_per_stage=8, stages=2, min_blocks=4)),
-    "c4": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(sn=16, rows_3d=4)),
-    # chunk 64 is best under sustained load (power cap); four x-adjacent warps per CTA read 4 % less from DRAM than two
-    "c5": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(sn=64, rows_3d=6, warps=4)),
+    # BASELINE.json configs (tuner records, see TUNED)
+    "c1": _tuned("c1"), "c2": _tuned("c2"), "c3": _tuned("c3"), "c4": _tuned("c4"), "c5": _tuned("c5"),
     # extra (not a BASELINE.json config): c4 with in-kernel temporal depth 2
     "c4t2": (_p("baseline", "c4_3d7pt_star.stc"), Knobs(step=2)),
     "c5t2": (_p("baseline", "c5_3d7pt_star.stc"), Knobs(step=2)),

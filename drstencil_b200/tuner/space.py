@@ -106,6 +106,73 @@ def cfg_to_string(c: Config) -> str:
     return s
 
 
+def cfg_from_string(name: str, dim: int) -> Config:
+    """Inverse of cfg_to_string: the configuration a result-file name denotes.  presets.py states the BASELINE
+    presets as such names, so that a preset IS a tuner record (profiles/r02_tune_*.json) and can be checked
+    against it."""
+    import re
+    rest = name
+    kw = dict(dim=dim)
+
+    def take(pattern):
+        nonlocal rest
+        m = re.match(pattern, rest)
+        if not m:
+            return None
+        rest = rest[m.end():]
+        return m
+
+    m = take(r"fu(\d+)d(\d+)bx(\d+)")
+    if not m:
+        raise ValueError("not a configuration name: %r" % name)
+    kw.update(step=int(m.group(1)), dist=int(m.group(2)), bx=int(m.group(3)))
+    if dim == 3:
+        m = take(r"y(\d+)sn(\d+)u(\d+)")
+        if not m:
+            raise ValueError("not a 3D configuration name: %r" % name)
+        kw.update(by=int(m.group(1)), sn=int(m.group(2)), s_unroll=int(m.group(3)), streaming=False)
+    else:
+        m = take(r"sn(\d+)u(\d+)")
+        if m:
+            kw.update(streaming=True, by=1, sn=int(m.group(1)), s_unroll=int(m.group(2)))
+        else:
+            m = take(r"y(\d+)")
+            if not m:
+                raise ValueError("not a 2D configuration name: %r" % name)
+            kw.update(streaming=False, by=int(m.group(1)))
+    m = take(r"(bmx|cmx)(\d+)")
+    kw.update(block_merge_x=m.group(1) == "bmx", mx=int(m.group(2)))
+    m = take(r"(bmy|cmy)(\d+)")
+    if m:
+        kw.update(block_merge_y=m.group(1) == "bmy", my=int(m.group(2)))
+    m = take(r"mf(\d+)")
+    kw.update(merge_forward=int(m.group(1)))
+    if take(r"p(?![a-z])"):
+        kw.update(prefetch=True)
+    m = take(r"st(\d+)")
+    if m:
+        kw.update(stages=int(m.group(1)))
+    m = take(r"mb(\d+)")
+    if m:
+        kw.update(min_blocks=int(m.group(1)))
+    m = take(r"ry(\d+)")
+    if m:
+        kw.update(rows_3d=int(m.group(1)))
+    m = take(r"sx(\d+)sy(\d+)")
+    if m:
+        kw.update(share_x=int(m.group(1)), share_y=int(m.group(2)))
+    if take(r"f32"):
+        kw.update(dtype="f32")
+    if take(r"alg"):
+        kw.update(fuse="algebraic")
+    if rest:
+        raise ValueError("trailing %r in configuration name %r" % (rest, name))
+    c = Config(**kw)
+    if cfg_to_string(c) != name:
+        raise ValueError("configuration name %r does not round-trip (%r)" % (name, cfg_to_string(c)))
+    return c
+
+
 def cfg_to_command_line(c: Config) -> str:
     """Arguments for the `drstencil` CLI that reproduce this configuration (tuning.py:50-69)."""
     cmd = " --step %d --dist %d --bx %d" % (c.step, c.dist, c.bx)
@@ -193,9 +260,10 @@ def filter_config(c: Config, dim: int, radius: int, esize: int = 8) -> bool:
 
 
 def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse: str = "temporal",
-                 experimental: bool = False) -> List[Config]:
-    """Cartesian product of the axes (reference: tuning.py:124-139), filtered.  `experimental` adds, for 3D
-    single-step sweeps, six rows per thread, longer chunks and the CTA-shared input ring (share_x x share_y)."""
+                 experimental: bool = True) -> List[Config]:
+    """Cartesian product of the axes (reference: tuning.py:124-139), filtered.  For 3D single-step sweeps the
+    space also holds six / eight / twelve rows per thread, longer chunks and the CTA-shared input ring
+    (share_x x share_y; `experimental=False` leaves those out)."""
     esize = 8 if dtype == "f64" else 4
     out = []
     if dim == 2:
@@ -214,7 +282,7 @@ def search_space(dim: int, radius: int, step: int = 1, dtype: str = "f64", fuse:
                 out.append(c)
         if experimental and step == 1:
             for (sx, sy), sn, ry, stages in itertools.product(
-                    ((1, 1), (2, 1), (1, 2), (2, 2), (3, 2), (2, 4)), (32, 64, 128), (4, 6, 8), (4, 8)):
+                    ((1, 1), (2, 1), (1, 2), (2, 2), (3, 2), (2, 4)), (32, 64, 128), (4, 6, 8, 12), (4, 8)):
                 warps = sx * sy if sx * sy > 1 else 4
                 c = Config(step=1, bx=32, by=warps, streaming=False, sn=sn, block_merge_y=True, my=1, rows_3d=ry,
                            stages=stages, dtype=dtype, fuse=fuse, share_x=sx, share_y=sy, dim=3)

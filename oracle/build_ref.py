@@ -72,16 +72,60 @@ def opt(opts, name, default):
     return int(opts[opts.index(name) + 1]) if name in opts else default
 
 
-def build(only=None, verbose=True):
-    if not os.path.isdir(REF):
-        print("build_ref: %s absent -- keeping prebuilt oracle/_ref" % REF)
-        return False
+def generator():
+    """oracle/_ref/drstencil_ref: the reference generator, built with its own Makefile line (Makefile:7)."""
     os.makedirs(os.path.join(OUT, "cases"), exist_ok=True)
     gen = os.path.join(OUT, "drstencil_ref")
     if not os.path.exists(gen):
         rc, out = sh(["g++", "-O3", "-std=c++17", "-w", "-o", gen, os.path.join(REF, "main.cpp")])
         if rc != 0:
             raise RuntimeError("reference generator failed to build:\n" + out)
+    return gen
+
+
+def build_one(case, stem, is3d, dims, iters, step, opts, cdir, so):
+    """One reference-emitted `--check` program (size-edited .stc -> drstencil_ref -> nvcc with the reference's
+    flags, sm_100a) wrapped by ref_wrap.cu into `so`.  Returns its metadata."""
+    gen = generator()
+    L, M, N = dims
+    os.makedirs(cdir, exist_ok=True)
+    # coefficient table taken from the shipped .stc, sizes edited in
+    src = os.path.join(REF, "benchmarks", stem, stem + ".stc")
+    toks = open(src).read().split()
+    body = toks[toks.index("stencil") + 1:]
+    w = 4 if is3d else 3
+    with open(os.path.join(cdir, stem + ".stc"), "w") as f:
+        if is3d:
+            f.write("L %d\n" % L)
+        f.write("M %d\nN %d\n\niterations %d\n\nstencil\n" % (M, N, iters))
+        for q in range(0, len(body), w):
+            f.write(" ".join(body[q:q + w]) + "\n")
+    args = [gen] + (["--3d"] if is3d else []) + ["--step", str(step)] + opts + \
+           ["--check", "-o", stem + ".cu", stem + ".stc"]
+    rc, out = sh(args, cwd=cdir)
+    cu = os.path.join(cdir, stem + ".cu")
+    if rc != 0 or not os.path.exists(cu):
+        raise RuntimeError("reference generator failed on %s (rc %d): %s" % (case, rc, out))
+    streaming = 1 if "--streaming" in opts else 0
+    mx = max(opt(opts, "--block-merge-x", 1), opt(opts, "--cyclic-merge-x", 1))
+    my = max(opt(opts, "--block-merge-y", 1), opt(opts, "--cyclic-merge-y", 1))
+    cmd = [NVCC, "-maxrregcount=128", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++11",
+           "--use_fast_math", "-Xptxas", "-dlcm=cg", "-w", "-shared", "-Xcompiler", "-fPIC",
+           "-Xlinker", "-Bsymbolic", "-I", REF, "-I", cdir,
+           '-DDRS_REF_CU="%s"' % cu, "-DDRS_REF_NAME=" + stem, "-DDRS_REF_3D=%d" % (1 if is3d else 0),
+           "-DDRS_REF_STREAMING=%d" % streaming, "-DDRS_REF_MX=%d" % mx, "-DDRS_REF_MY=%d" % my,
+           "-DDRS_REF_STEP=%d" % step, "-o", so, os.path.join(HERE, "ref_wrap.cu")]
+    rc, out = sh(cmd)
+    if rc != 0:
+        raise RuntimeError("nvcc failed on %s:\n%s" % (case, out))
+    return dict(stencil=stem, is3d=is3d, L=L, M=M, N=N, iterations=iters, step=step, options=opts)
+
+
+def build(only=None, verbose=True):
+    if not os.path.isdir(REF):
+        print("build_ref: %s absent -- keeping prebuilt oracle/_ref" % REF)
+        return False
+    generator()
     meta = {}
     meta_path = os.path.join(OUT, "cases.json")
     if os.path.exists(meta_path):
@@ -90,41 +134,11 @@ def build(only=None, verbose=True):
         if only and case not in only:
             continue
         so = os.path.join(OUT, "libref_%s.so" % case)
-        if os.path.exists(so) and case in meta:
+        if os.path.exists(so) and case in meta and meta[case].get("options") == opts:
             continue
-        cdir = os.path.join(OUT, "cases", case)
-        os.makedirs(cdir, exist_ok=True)
-        # coefficient table taken from the shipped .stc, sizes edited in
-        src = os.path.join(REF, "benchmarks", stem, stem + ".stc")
-        toks = open(src).read().split()
-        body = toks[toks.index("stencil") + 1:]
-        w = 4 if is3d else 3
-        with open(os.path.join(cdir, stem + ".stc"), "w") as f:
-            if is3d:
-                f.write("L %d\n" % L)
-            f.write("M %d\nN %d\n\niterations %d\n\nstencil\n" % (M, N, iters))
-            for q in range(0, len(body), w):
-                f.write(" ".join(body[q:q + w]) + "\n")
-        args = [gen] + (["--3d"] if is3d else []) + ["--step", str(step)] + opts + \
-               ["--check", "-o", stem + ".cu", stem + ".stc"]
-        rc, out = sh(args, cwd=cdir)
-        cu = os.path.join(cdir, stem + ".cu")
-        if rc != 0 or not os.path.exists(cu):
-            raise RuntimeError("reference generator failed on %s (rc %d): %s" % (case, rc, out))
-        streaming = 1 if "--streaming" in opts else 0
-        mx = max(opt(opts, "--block-merge-x", 1), opt(opts, "--cyclic-merge-x", 1))
-        my = max(opt(opts, "--block-merge-y", 1), opt(opts, "--cyclic-merge-y", 1))
-        cmd = [NVCC, "-maxrregcount=128", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++11",
-               "--use_fast_math", "-Xptxas", "-dlcm=cg", "-w", "-shared", "-Xcompiler", "-fPIC",
-               "-Xlinker", "-Bsymbolic", "-I", REF, "-I", cdir,
-               '-DDRS_REF_CU="%s"' % cu, "-DDRS_REF_NAME=" + stem, "-DDRS_REF_3D=%d" % (1 if is3d else 0),
-               "-DDRS_REF_STREAMING=%d" % streaming, "-DDRS_REF_MX=%d" % mx, "-DDRS_REF_MY=%d" % my,
-               "-DDRS_REF_STEP=%d" % step, "-o", so, os.path.join(HERE, "ref_wrap.cu")]
-        rc, out = sh(cmd)
-        if rc != 0:
-            raise RuntimeError("nvcc failed on %s:\n%s" % (case, out))
-        meta[case] = dict(stencil=stem, is3d=is3d, L=L, M=M, N=N, iterations=iters, step=step, options=opts,
-                          so="libref_%s.so" % case, cu="cases/%s/%s.cu" % (case, stem))
+        meta[case] = build_one(case, stem, is3d, (L, M, N), iters, step, opts, os.path.join(OUT, "cases", case), so)
+        meta[case]["so"] = "libref_%s.so" % case
+        meta[case]["cu"] = "cases/%s/%s.cu" % (case, stem)
         if verbose:
             print("build_ref: built", case)
         json.dump(meta, open(meta_path, "w"), indent=1, sort_keys=True)

@@ -81,11 +81,29 @@ def test_emitted_program_is_self_contained_text(built, tmp_path):
         assert needle in text, needle
 
 
+def test_emitted_program_runs_every_sub_step_of_an_unfused_3d_temporal_sweep(built, tmp_path):
+    """`--3d --step 5 --fuse temporal` is too deep for the fused kernel: one sweep = five single-step launches with
+    frozen rings r, 2r, ... (KernelSpec::sub_launches).  The emitted program must do the same (round 1: it launched
+    once per sweep, advanced one timestep instead of five and failed its own --check)."""
+    shutil.copy(os.path.join(ROOT, "stc", "3d7pt_star.stc"), tmp_path)
+    rc, out = _run(CLI, ["--3d", "--step", "5", "--fuse", "temporal", "--check", "-o", "x.cu", "3d7pt_star.stc"], tmp_path)
+    assert rc == 0, out
+    text = open(tmp_path / "x.cu").read()
+    assert "#define Halo 5" in text and "#define Step 5" in text
+    assert "for (int s = 1; s <= 5; ++s)" in text and "dr_launch_one(src, dst, s * 1);" in text
+    assert "scratch[(s - 1) & 1]" in text
+    # a fused (or single-step) program launches once per sweep
+    rc, out = _run(CLI, ["--3d", "--step", "2", "--check", "-o", "y.cu", "3d7pt_star.stc"], tmp_path)
+    assert rc == 0, out
+    assert "dr_launch_one(in, out, Halo);" in open(tmp_path / "y.cu").read()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("argv,name,exact", [
     (["--check"], "2d5pt_star", True),
     (["--step", "2", "--check"], "2d9pt_box", False),
     (["--3d", "--check"], "3d7pt_star", True),
+    (["--3d", "--step", "5", "--fuse", "temporal", "--check"], "3d7pt_star", False),
 ])
 def test_emitted_program_builds_and_checks_out_on_gpu(built, tmp_path, argv, name, exact):
     """`drstencil ... -o out.cu` -> nvcc -> run: the reference's stdout protocol, error at the floor."""

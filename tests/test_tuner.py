@@ -34,6 +34,22 @@ def test_config_name_grammar_matches_reference():
     assert cfg_to_string(c) == "fu4d0bx64sn256u4bmx2mf5st8mb4f32alg"
 
 
+def test_config_names_round_trip_and_presets_are_tuner_names():
+    """A result-file name denotes exactly one configuration (cfg_from_string o cfg_to_string = id over the whole
+    space), and every BASELINE preset is stated as such a name (presets.TUNED)."""
+    from drstencil_b200.tuner.space import cfg_from_string, cfg_to_string, search_space
+    for dim, radius, step, dtype in ((2, 1, 1, "f64"), (2, 1, 4, "f64"), (2, 2, 1, "f32"), (3, 1, 1, "f64"), (3, 1, 2, "f64")):
+        for c in search_space(dim, radius, step, dtype):
+            assert cfg_from_string(cfg_to_string(c), dim) == c
+    from drstencil_b200.presets import PRESETS, TUNED
+    for wl, (path, dim, name) in TUNED.items():
+        c = cfg_from_string(name, dim)
+        assert repr(c.knobs()) == repr(PRESETS[wl][1])
+    import pytest
+    with pytest.raises(ValueError):
+        cfg_from_string("fu1d0bx64sn128u4bmx2mf5st2zz", 2)
+
+
 def test_search_space_filter():
     from drstencil_b200.tuner.space import Config, filter_config, search_space
     sp = search_space(2, 1, step=4)
