@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libdrstencil.so")
 
 F64, F32 = 0, 1
-FUSE_TEMPORAL, FUSE_ALGEBRAIC = 0, 1
+FUSE_TEMPORAL, FUSE_ALGEBRAIC, FUSE_REUSE = 0, 1, 2
 E_ARG, E_IO, E_NOREUSE, E_CONFIG, E_COMPILE, E_CUDA, E_NOGPU, E_KERNEL = -1, -2, -3, -4, -5, -6, -7, -8
 
 
@@ -66,15 +66,8 @@ def lib():
     if not os.path.exists(_LIBPATH):
         raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(or drstencil_b200.build())" % _LIBPATH)
-    # libdrstencil.so dlopen()s "libnvrtc.so.12"; if torch is imported later (or earlier) in the same process
-    # that name resolves to the copy torch ships (12.8 here) or to the toolkit's (12.9) depending on the ORDER of
-    # the imports, and the two compilers do not produce the same cubins (the cache key carries the version).
-    # Importing torch first pins one answer for build(), tests, bench and tools alike -- the one every GPU
-    # measurement of this repo was taken with.
-    try:
-        import torch  # noqa: F401
-    except ImportError:
-        pass
+    # The library dlopen()s ONE pinned NVRTC by absolute path (csrc/capi/capi.cpp, _build.pinned_nvrtc), so the
+    # cubins no longer depend on whether torch was imported first (round 1: two compilers, two sets of cubins).
     L = ctypes.CDLL(_LIBPATH)
     vp, i32, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
     P = ctypes.POINTER
@@ -126,6 +119,7 @@ def lib():
         "drs_emit_program": (i32, [vp, P(_CKnobs), ctypes.c_char_p, ctypes.c_char_p]),
         "drs_last_error": (ctypes.c_char_p, []),
         "drs_version": (ctypes.c_char_p, []),
+        "drs_compiler": (ctypes.c_char_p, []),
         "drs_device_count": (i32, []),
         "drs_set_device": (i32, [i32]),
         "drs_set_cache_dir": (None, [ctypes.c_char_p]),
@@ -196,7 +190,7 @@ class Knobs:
         if name == "dtype" and isinstance(value, str):
             value = {"f64": F64, "fp64": F64, "double": F64, "f32": F32, "fp32": F32, "float": F32}[value]
         if name == "fuse" and isinstance(value, str):
-            value = {"temporal": FUSE_TEMPORAL, "algebraic": FUSE_ALGEBRAIC}[value]
+            value = {"temporal": FUSE_TEMPORAL, "algebraic": FUSE_ALGEBRAIC, "reuse": FUSE_REUSE}[value]
         if name in self.extra:
             self.extra[name] = int(value)
         elif name in self.values:

@@ -110,7 +110,7 @@ std::string cu_err(CUresult r) {
 // ---------------------------------------------------------------------------------------------
 struct Nvrtc {
     bool ok = false;
-    std::string why;
+    std::string why, path;
     void* h = nullptr;
     typedef struct _nvrtcProgram* Prog;
     int (*CreateProgram)(Prog*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
@@ -128,11 +128,21 @@ Nvrtc& nvrtc() {
     static Nvrtc n;
     static std::once_flag once;
     std::call_once(once, [] {
-        const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
-                               "/usr/local/cuda/lib64/libnvrtc.so"};
-        for (const char* nm : names) {
-            n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
-            if (n.h) break;
+        // ONE compiler for every consumer of the library (Python, the C++ CLI, C hosts): the copy pinned at build
+        // time (DRS_NVRTC_PINNED, an absolute path: _build.py picks the one every measurement of this repo was
+        // taken with), not whatever "libnvrtc.so.12" happens to resolve to in the process -- that depended on
+        // whether torch had been imported first, and the two copies in this image (12.8 / 12.9) do not produce the
+        // same cubins.  DRS_NVRTC=<path> overrides; the bare names are the fallback for other installations.
+        std::vector<std::string> names;
+        if (const char* e = getenv("DRS_NVRTC")) names.push_back(e);
+#ifdef DRS_NVRTC_PINNED
+        names.push_back(DRS_NVRTC_PINNED);
+#endif
+        for (const char* nm : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+            names.push_back(nm);
+        for (const std::string& nm : names) {
+            n.h = dlopen(nm.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (n.h) { n.path = nm; break; }
         }
         if (!n.h) { n.why = "libnvrtc.so.12 not found"; return; }
         auto get = [&](const char* name) { return dlsym(n.h, name); };
@@ -322,7 +332,12 @@ int ensure_loaded(drs_plan* p) {
     CUresult r = d.ModuleLoadData(&p->mod, p->cubin.data());
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleLoadData: " + cu_err(r));
     const std::string nm = p->spec.name;
-    if (p->spec.tma_ok) {
+    if (p->spec.reuse) {
+        r = d.ModuleGetFunction(&p->f_sweep, p->mod, ("dr_" + nm).c_str());
+        if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(dr_): " + cu_err(r));
+        d.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->f_sweep);
+        d.FuncGetAttribute(&p->spill, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, p->f_sweep);
+    } else if (p->spec.tma_ok) {
         r = d.ModuleGetFunction(&p->f_sweep, p->mod, ("dr_" + nm).c_str());
         if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(dr_): " + cu_err(r));
         const int smem = p->spec.smem_bytes();
@@ -364,11 +379,13 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     CUtensorMapL2promotion promo = s.dim == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char* e = getenv("DRS_TMA_L2PROMO")) promo = (CUtensorMapL2promotion)atoi(e);
     if (s.flat) {
-        // one flat 1D tensor over the whole array; a tile is fetched as one box of wb() elements per row
-        cuuint64_t dims[1] = {(cuuint64_t)p->st.L * (cuuint64_t)p->st.M * (cuuint64_t)p->st.N};
-        cuuint32_t box[1] = {(cuuint32_t)s.wb()};
-        cuuint32_t estr[1] = {1};
-        r = driver().TensorMapEncodeTiled(&m, dt, 1, const_cast<void*>(base), dims, nullptr, box, estr,
+        // the whole array as one row of a {total, 1} tensor; a tile is fetched as one box of wb() elements per row
+        const cuuint64_t total = (cuuint64_t)p->st.L * (cuuint64_t)p->st.M * (cuuint64_t)p->st.N;
+        cuuint64_t dims[2] = {total, 1};
+        cuuint64_t strides[1] = {(total * es + 15) / 16 * 16};      // never used (one row), but must be a multiple of 16
+        cuuint32_t box[2] = {(cuuint32_t)s.wb(), 1};
+        cuuint32_t estr[2] = {1, 1};
+        r = driver().TensorMapEncodeTiled(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                           promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else if (s.dim == 2) {
@@ -484,8 +501,33 @@ int launch_gold(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
 int launch_one(drs_plan* p, const void* in, void* out, cudaStream_t stream, int ring, const SlowRange* sub = nullptr,
                int seq_off = -1);
 
+// `--fuse reuse` (drs_reuse.cuh): the reference's launch shape -- overlapped tiles of bx x by threads, one block
+// per tile and chunk of `sn` slow-axis outputs (codegen_2d.hpp:585-598, codegen.hpp:566-571)
+int launch_reuse(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
+    const drs::KernelSpec& s = p->spec;
+    DevParams q;
+    fill_params(p, in, out, q);
+    void* args[] = {&q};
+    const long long H = s.halo;
+    const long long nslow = (q.slow_hi - q.slow_lo + s.chunk - 1) / s.chunk;
+    if (nslow <= 0 || q.N <= 2 * H) return DRS_OK;
+    const unsigned gx = (unsigned)((q.N - 2 * H + (s.rbx - 2 * H) - 1) / (s.rbx - 2 * H));
+    unsigned gy, gz;
+    if (s.dim == 3) {
+        if (q.M <= 2 * H) return DRS_OK;
+        gy = (unsigned)((q.M - 2 * H + (s.rby - 2 * H) - 1) / (s.rby - 2 * H));
+        gz = (unsigned)nslow;
+    } else { gy = (unsigned)nslow; gz = 1; }
+    if (gy > 65535u || gz > 65535u) return fail(DRS_E_ARG, "grid too large for the data-reuse mode: raise --sn");
+    CUresult r = driver().LaunchKernel(p->f_sweep, gx, gy, gz, (unsigned)s.rbx, (unsigned)s.rby, 1, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "launch dr_ (data reuse): " + cu_err(r));
+    p->launches++;
+    return DRS_OK;
+}
+
 int launch_sweep(drs_plan* p, const void* in, void* out, cudaStream_t stream) {
     if (in == out) return fail(DRS_E_ARG, "d_in and d_out must differ");
+    if (p->spec.reuse) return launch_reuse(p, in, out, stream);
     if (!p->spec.tma_ok) return launch_gold(p, in, out, stream);
     const int T = p->spec.sub_launches;
     if (T <= 1) return launch_one(p, in, out, stream, -1);
@@ -540,7 +582,13 @@ int make_plan(const drs_stencil* s, const drs_knobs* k, drs_plan** out, bool com
     p->knobs = *k;
     p->spec.name = s->name;
     std::string err = drs::choose_spec(s->st, *k, p->spec);
-    if (!err.empty()) { delete p; return fail(DRS_E_ARG, err); }
+    if (!err.empty()) {
+        delete p;
+        // `--fuse reuse` refuses what the reference refuses, with its messages (drstencil_2d.hpp:217-220, codegen_2d.hpp:52-56)
+        if (err.rfind("NOREUSE:", 0) == 0) return fail(DRS_E_NOREUSE, err.substr(8));
+        if (err.rfind("CONFIG:", 0) == 0) return fail(DRS_E_CONFIG, err.substr(7));
+        return fail(DRS_E_ARG, err);
+    }
     p->source = drs::generate_tu(p->spec);
     if (compile) {
         rc = compile_cubin(p->source, p->cubin, p->cache_key);
@@ -707,7 +755,12 @@ int drs_plan_get_info(const drs_plan* p, drs_plan_info* info) {
     else computed = (double)q.nxs * s.wt() * (double)q.nys * s.tile_rows() *
                     ((double)(q.slow_hi - q.slow_lo) + (s.fused3d ? (double)q.nzs * (2 * s.ts * s.rk + s.ts - 1) : 0.0));
     info->redundancy = computed / useful;
-    std::snprintf(info->kernel_name, sizeof info->kernel_name, "%s%s", s.tma_ok ? "dr_" : "gold_", s.name.c_str());
+    std::snprintf(info->kernel_name, sizeof info->kernel_name, "%s%s", (s.tma_ok || s.reuse) ? "dr_" : "gold_", s.name.c_str());
+    if (s.reuse) {
+        info->warps_per_cta = (s.rbx * s.rby + 31) / 32; info->tile_x = s.rbx - 2 * s.halo; info->tile_y = s.dim == 3 ? s.rby - 2 * s.halo : 1;
+        info->block = s.rbx * s.rby; info->stages = 0; info->smem_bytes = 0;
+        info->redundancy = (double)s.rbx / std::max(1, s.rbx - 2 * s.halo) * (s.dim == 3 ? (double)s.rby / std::max(1, s.rby - 2 * s.halo) : 1.0);
+    }
     return DRS_OK;
 }
 
@@ -1338,7 +1391,15 @@ int drs_emit_program(const drs_stencil* s, const drs_knobs* k, const char* kerne
 }
 
 const char* drs_last_error(void) { return g_err.c_str(); }
-const char* drs_version(void) { return "drstencil-b200 0.1 (sm_100a)"; }
+const char* drs_version(void) { return "drstencil-b200 0.2 (sm_100a)"; }
+const char* drs_compiler(void) {
+    static std::string text;
+    Nvrtc& n = nvrtc();
+    int maj = 0, min = 0;
+    if (n.ok) n.Version(&maj, &min);
+    text = n.ok ? "NVRTC " + std::to_string(maj) + "." + std::to_string(min) + " (" + n.path + ")" : "NVRTC unavailable: " + n.why;
+    return text.c_str();
+}
 int drs_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -49,7 +49,13 @@ static double check_result(const real_t* out, const real_t* ref) {   // common.h
                 double d = (double)out[(kk * GridM + j) * GridN + i] - (double)ref[(kk * GridM + j) * GridN + i];
                 d = d < 0.0 ? -d : d;
                 error += d * d;
-                if (d > max_error) { max_error = d; mk = kk; mj = j; mi = i; }
+                if (d > max_error) {
+                    if (DRS_DIM == 3) printf("Values at index (%lld,%lld,%lld) differ : %.6f and %.6f\n", kk, j, i,
+                                             (double)ref[(kk * GridM + j) * GridN + i], (double)out[(kk * GridM + j) * GridN + i]);
+                    else printf("Values at index (%lld,%lld) differ : %.6f and %.6f\n", j, i,
+                                (double)ref[(kk * GridM + j) * GridN + i], (double)out[(kk * GridM + j) * GridN + i]);
+                    max_error = d; mk = kk; mj = j; mi = i;
+                }
             }
     if (DRS_DIM == 3) printf("[Test] Max Error : %e @ (%lld,%lld,%lld)\n", max_error, mk, mj, mi);
     else printf("[Test] Max Error : %e @ (,%lld,%lld)\n", max_error, mj, mi);
@@ -77,7 +83,19 @@ static void gold_launch(const real_t* in, real_t* out) {
     DRS_GOLD_NAME<<<grid, block>>>(p);
 }
 )";
-    if (s.tma_ok) {
+    if (s.reuse) {
+        // the reference's launch shape: overlapped bx x by tiles, one block per tile and chunk (codegen_2d.hpp:585-598)
+        o << "static void dr_launch(const real_t* in, real_t* out) {\n"
+             "    drs::Params p = make_params(in, out);\n";
+        o << "    dim3 block(" << s.rbx << ", " << s.rby << ", 1);\n";
+        o << "    const long long nslow = (p.slow_hi - p.slow_lo + p.chunk - 1) / p.chunk;\n";
+        o << "    const unsigned gx = (unsigned)((GridN - 2 * Halo + " << (s.rbx - 2 * s.halo - 1) << ") / " << (s.rbx - 2 * s.halo) << ");\n";
+        if (s.dim == 3)
+            o << "    dim3 grid(gx, (unsigned)((GridM - 2 * Halo + " << (s.rby - 2 * s.halo - 1) << ") / " << (s.rby - 2 * s.halo) << "), (unsigned)nslow);\n";
+        else
+            o << "    dim3 grid(gx, (unsigned)nslow, 1);\n";
+        o << "    DRS_NAME<<<grid, block>>>(p);\n}\n";
+    } else if (s.tma_ok) {
         o << "static CUtensorMap make_map(const real_t* base) {\n"
              "    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,\n"
              "        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,\n"
@@ -89,9 +107,10 @@ static void gold_launch(const real_t* in, real_t* out) {
              "    CUtensorMap m;\n";
         o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
         if (s.flat) {
-            o << "    cuuint64_t dims[1] = {(cuuint64_t)GridL * GridM * GridN}; cuuint64_t* strides = 0;\n";
-            o << "    cuuint32_t box[1] = {" << s.wb() << "}; cuuint32_t es[1] = {1};\n";
-            o << "    CUresult r = encode(&m, dt, 1, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            o << "    cuuint64_t dims[2] = {(cuuint64_t)GridL * GridM * GridN, 1};\n"
+                 "    cuuint64_t strides[1] = {(dims[0] * sizeof(real_t) + 15) / 16 * 16};\n";
+            o << "    cuuint32_t box[2] = {" << s.wb() << ", 1}; cuuint32_t es[2] = {1, 1};\n";
+            o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
         } else if (s.dim == 2) {
             o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
             o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
@@ -156,7 +175,7 @@ int main(int argc, char** argv)
     cudaMemcpy(out, h_out, nbytes, cudaMemcpyHostToDevice);
     cudaMalloc(&g_fault, sizeof(int)); cudaMemset(g_fault, 0, sizeof(int));
 )";
-    if (s.tma_ok)
+    if (s.tma_ok && !s.reuse)
         o << "    cudaFuncSetAttribute(DRS_NAME, cudaFuncAttributeMaxDynamicSharedMemorySize, " << s.smem_bytes() << ");\n";
     o << R"(
     puts("GPU computing ...");

@@ -54,6 +54,10 @@ struct KernelSpec {
     std::vector<double> fw;                 // w[dj + rj]
     std::vector<Term> fres;                 // residual terms (coefficient = K - w*h where that is not zero)
     int fops = 0;                           // arithmetic operations per output in factored form
+    // `--fuse reuse`: the reference's forward/backward evaluation (drs_reuse.cuh); block shape rbx x rby
+    bool reuse = false;
+    int dist = 0, rbx = 128, rby = 1;
+    std::vector<Term> fwd_slow, fwd_mid, fwd_fast, bwd;
     std::string name = "stencil";
     std::string note;           // why a requested mode was changed, for logs
 
@@ -128,6 +132,33 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     comp.compose(k.step);
     s.gold = comp.terms();
     const int vec = s.vec();
+    if (k.fuse == DRS_FUSE_REUSE) {
+        // the reference's own scheme on the composed operator, with its own knobs and its own refusals
+        Analysis a;
+        if (!comp.analyze(k.dist, k.merge_forward, a)) return "NOREUSE:No data to reuse. You can try another dist.";
+        s.reuse = true;
+        s.dist = a.dist;
+        s.ts = 1;
+        s.chain = s.gold;
+        s.base_order = order;
+        for (const Term& t : s.chain) {
+            s.rk = std::max(s.rk, std::abs(t.dk)); s.rj = std::max(s.rj, std::abs(t.dj)); s.e = std::max(s.e, std::abs(t.di));
+        }
+        s.fwd_slow = comp.partial_sum(a, 0); s.fwd_mid = comp.partial_sum(a, 1);
+        s.fwd_fast = comp.partial_sum(a, 2); s.bwd = comp.partial_sum(a, 3);
+        s.rbx = knob_given(k, KB_BX) ? k.bx : (s.dim == 2 ? 128 : 32);
+        s.rby = s.dim == 3 ? (knob_given(k, KB_BY) ? k.by : 8) : 1;
+        s.chunk = knob_given(k, KB_SN) && k.sn > 0 ? k.sn : 32;
+        // codegen_2d.hpp:52-56, codegen.hpp:50-55: tiles that do not cover the halo while a cross-thread forward exists
+        if ((2 * s.halo >= s.rbx && !s.fwd_fast.empty()) || (s.dim == 3 && 2 * s.halo >= s.rby && !s.fwd_mid.empty()))
+            return "CONFIG:Invalid configuration!";
+        if (s.rbx <= 2 * s.halo || (s.dim == 3 && s.rby <= 2 * s.halo) || s.rbx * s.rby > 1024 || s.rbx < 1 || s.rby < 1)
+            return "CONFIG:Invalid configuration!";
+        if (s.dist > s.halo) return "CONFIG:Invalid configuration!";
+        s.tma_ok = false;
+        s.flat = false;
+        return "";
+    }
     s.flat = (st.N % vec) != 0;   // row pitch not a multiple of 16 bytes -> flat 1D tensor map (drs_common.cuh)
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
     if (temporal) {
@@ -457,7 +488,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     std::ostringstream o;
     o << "// generated by drstencil-b200 for sm_100a -- stencil '" << s.name << "', " << (s.dim == 3 ? "3D" : "2D")
       << ", " << (s.dtype == DRS_F64 ? "fp64" : "fp32") << ", step " << s.step << " ("
-      << (s.ts > 1 ? "temporal" : (s.step > 1 ? "algebraic" : "single")) << ")\n";
+      << (s.reuse ? "forward/backward data reuse" : s.ts > 1 ? "temporal" : (s.step > 1 ? "algebraic" : "single")) << ")\n";
     o << "#define DRS_DIM " << s.dim << "\n";
     o << "#define DRS_T " << (s.dtype == DRS_F64 ? "double" : "float") << "\n";
     o << "#define DRS_NAME dr_" << s.name << "\n";
@@ -484,11 +515,22 @@ inline std::string generate_tu(const KernelSpec& s) {
             o << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
         }
     }
+    if (s.reuse) {
+        o << "#define DRS_DIST " << s.dist << "\n#define DRS_RBX " << s.rbx << "\n#define DRS_RBY " << s.rby << "\n";
+        emit_chain(o, "DRS_FWD_SLOW", s.fwd_slow);
+        o << "#define DRS_HAS_BWD " << (s.bwd.empty() ? 0 : 1) << "\n";
+        if (!s.bwd.empty()) emit_chain(o, "DRS_BWD", s.bwd);
+        o << "#define DRS_HAS_FWD_MID " << (s.fwd_mid.empty() ? 0 : 1) << "\n";
+        if (!s.fwd_mid.empty()) emit_chain(o, "DRS_FWD_MID", s.fwd_mid);
+        o << "#define DRS_HAS_FWD_FAST " << (s.fwd_fast.empty() ? 0 : 1) << "\n";
+        if (!s.fwd_fast.empty()) emit_chain(o, "DRS_FWD_FAST", s.fwd_fast);
+    }
     emit_chain(o, "DRS_CHAIN", s.chain);
     if (s.ts > 1 && s.dim == 2) emit_scatter(o, s);
     if (s.fused3d) emit_scatter3(o, s);
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
-    if (s.tma_ok)
+    if (s.reuse) o << "#include \"drs_reuse.cuh\"\n";
+    else if (s.tma_ok)
         o << "#include \"" << (s.fused3d ? "drs_sweep3d_t.cuh" : s.share3d ? "drs_sweep3d_cta.cuh" : s.dim == 3 ? "drs_sweep3d.cuh" : "drs_sweep2d.cuh") << "\"\n";
     o << "#include \"drs_gold.cuh\"\n";
     return o.str();

@@ -211,6 +211,22 @@ class Stencil {
         return true;
     }
 
+    // The partial sums of the partition as the reference prints them (gen_forward_j / gen_forward_i /
+    // gen_backward, drstencil_2d.hpp:120-162): a forward term reads the input at the point's offset but carries
+    // the coefficient of the point `dist` earlier along its axis; set order == evaluation order.
+    // which: 0 forward_slow, 1 forward_mid, 2 forward_fast, 3 backward.
+    std::vector<Term> partial_sum(const Analysis& a, int which) const {
+        const PointSet& set = which == 0 ? a.forward_slow : which == 1 ? a.forward_mid : which == 2 ? a.forward_fast : a.backward;
+        std::vector<Term> t;
+        for (const Point& p : set) {
+            const Point q = which == 3 ? p : shifted(p, which, -a.dist);
+            const auto it = points.find(q);
+            const double c = it == points.end() ? 0.0 : it->second;
+            t.push_back({std::get<0>(p), std::get<1>(p), std::get<2>(p), coef_literal_value(c)});
+        }
+        return t;
+    }
+
    private:
     int slow(const Point& p) const { return dim == 3 ? std::get<0>(p) : std::get<1>(p); }
     // axis: 0 slow, 1 middle (3D only), 2 fast

@@ -205,10 +205,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
+// DRS_FLAT: the array as a {total, 1} tensor (rank 2 keeps the encoder's stride array non-empty); x = flat element index
 __device__ __forceinline__ void tma_load_1d(void* dst, const TensorMap* map, int x, drs_u64* bar) {
     asm volatile(
-        "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(smem_u32(bar))
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(0), "r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {

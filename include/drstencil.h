@@ -37,6 +37,10 @@ extern "C" {
 #define DRS_FUSE_TEMPORAL 0   /* --step n = n in-kernel sub-steps of the base operator          */
 #define DRS_FUSE_ALGEBRAIC 1  /* --step n = the composed (fused) operator evaluated literally,   */
                               /*            exactly what the reference emits                    */
+#define DRS_FUSE_REUSE 2      /* A/B mode: the composed operator through the reference's forward / */
+                              /* backward data-reuse scheme (drstencil_2d.hpp:180-228): store the  */
+                              /* forward sum Dist rows ahead, add the backward sum (csrc/kernels/  */
+                              /* drs_reuse.cuh); honours --dist / --merge-forward / --bx/--by/--sn */
 
 typedef struct drs_stencil drs_stencil; /* DRStencil_2d / DRStencil (drstencil_2d.hpp:14-45, drstencil.hpp:14-49) */
 typedef struct drs_plan drs_plan;       /* one specialised, compiled sweep == one emitted dr_<name> + its launch shape */
@@ -239,6 +243,8 @@ int drs_emit_program(const drs_stencil *s, const drs_knobs *k, const char *kerne
 /* ---- misc -------------------------------------------------------------------------------- */
 const char *drs_last_error(void);
 const char *drs_version(void);
+/* which NVRTC the library compiles its kernels with ("NVRTC 12.8 (<path>)"): one pinned copy for every consumer */
+const char *drs_compiler(void);
 int drs_device_count(void);
 /* makes CUDA device `ordinal` current for the calling thread (one process per GPU: LOCAL_RANK); a plan is bound
  * to the device that is current at its first sweep */

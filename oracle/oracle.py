@@ -266,6 +266,48 @@ def sweep(inp: np.ndarray, out: np.ndarray, offs: np.ndarray, coefs: np.ndarray,
        out.ctypes.data, 1 if contract else 0)
 
 
+def sweep_reuse(inp: np.ndarray, out: np.ndarray, points: dict, dim: int, dist_opt: int = 0, merge_forward: int = 5) -> bool:
+    """The reference's data-reuse evaluation of one sweep (its dr_<name> kernel, codegen_2d.hpp:345-366,
+    codegen.hpp:391-427): out = ((forward_slow + backward) + forward_mid) + forward_fast on the interior, every
+    partial sum being the contracted chain of its own terms (a forward term reads the input at its point's offset with
+    the coefficient of the point `Dist` earlier along its axis: gen_forward_j, drstencil_2d.hpp:120-135).  The
+    reference's two cross-thread atomics can land in either order; this is the order the engine's A/B kernel fixes.
+    Returns False where the reference exits with "No data to reuse"."""
+    halo, dist = order_dist(points, dim, dist_opt)
+    part = partition(points, dim, dist, merge_forward)
+    if part is None:
+        return False
+    ax_slow = 0 if dim == 3 else 1
+
+    def partial(pts, axis):
+        keys = sorted(pts)
+        if not keys:
+            return None
+        # seen from the OUTPUT point a forward term p is simply the stencil point q = p - Dist*e with its own
+        # coefficient (the sweep is centred Dist rows before the output it forwards to); the partition decides
+        # the grouping and the order of the sum, not the operands
+        qs = []
+        for p in keys:
+            q = list(p)
+            if axis is not None:
+                q[axis] -= dist
+            qs.append(tuple(q))
+        offs = np.array(qs, dtype=np.int32).reshape(-1, 3)
+        co = np.array([literal(points[q]) for q in qs], dtype=np.float64)
+        tmp = np.zeros_like(inp)
+        sweep(inp, tmp, offs, co, halo)
+        return tmp
+
+    inner = tuple(slice(halo, n - halo) for n in inp.shape)
+    acc = partial(part["forward_slow"], ax_slow)
+    for pts, axis in ((part["backward"], None), (part["forward_mid"], 1), (part["forward_fast"], 2)):
+        t = partial(pts, axis)
+        if t is not None:
+            acc = acc + t          # IEEE round-to-nearest add of the rounded partial sums (atomicAdd / RED.ADD)
+    out[inner] = acc[inner]
+    return True
+
+
 def run(A: np.ndarray, B: np.ndarray, offs, coefs, halo: int, iterations: int, step: int,
         contract: bool = True) -> int:
     """The emitted program's ping-pong schedule; result ends in A.  Returns sweeps done."""

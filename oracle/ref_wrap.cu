@@ -106,11 +106,65 @@ float drs_ref_time(int which, int sweeps, int warm) {
     }
     cudaEventRecord(e1);
     cudaError_t e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();      // e.g. an invalid launch shape: nothing ran
     float ms = -1.f;
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d[0]); cudaFree(d[1]);
     return ms;
+}
+
+// The reference's own acceptance test (its --check: dr_ against gold_ through the same schedule, common.hpp:47-102)
+// on device-generated input, compared on the device: returns the largest |dr - gold| over the whole array after
+// `sweeps` ping-pong launches each, or < 0 when a launch fails.  Used by oracle/tune_ref.py to reject candidates of
+// the reference's search space that do not run (or do not compute the stencil) on this GPU.
+__global__ void drs_ref_fill(double *a, size_t n) {
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        unsigned long long s = (unsigned long long)x * 6364136223846793005ULL + 1442695040888963407ULL;
+        s ^= s >> 33; s *= 0xff51afd7ed558ccdULL; s ^= s >> 33;
+        a[x] = (double)(s >> 11) * (1.0 / 9007199254740992.0);
+    }
+}
+__global__ void drs_ref_maxdiff(const double *a, const double *b, size_t n, unsigned long long *res) {
+    double m = 0.0;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        double d = a[x] - b[x];
+        d = d < 0.0 ? -d : d;
+        if (!(d <= m)) m = d;          // NaN counts as a failure
+    }
+    if (m != m) m = 1e300;
+    atomicMax(res, (unsigned long long)__double_as_longlong(m));
+}
+double drs_ref_check(int sweeps) {
+    size_t n = (size_t)DRS_L * M * N, nbytes = sizeof(double) * n;
+    double *d[4] = {0, 0, 0, 0};
+    unsigned long long *res = 0;
+    for (int x = 0; x < 4; ++x)
+        if (cudaMalloc(&d[x], nbytes) != cudaSuccess) { for (int y = 0; y < x; ++y) cudaFree(d[y]); cudaGetLastError(); return -1.0; }
+    cudaMalloc(&res, sizeof *res);
+    cudaMemset(res, 0, sizeof *res);
+    drs_ref_fill<<<1184, 256>>>(d[0], n);
+    cudaMemcpy(d[2], d[0], nbytes, cudaMemcpyDeviceToDevice);
+    cudaMemset(d[1], 0, nbytes); cudaMemset(d[3], 0, nbytes);
+    dim3 grid, block, ggrid, gblock;
+    dr_launch_shape(grid, block);
+    gold_launch_shape(ggrid, gblock);
+    for (int s = 0; s < sweeps; ++s) {
+        DR_KERNEL<<<grid, block>>>(d[s & 1], d[(s & 1) ^ 1]);
+        GOLD_KERNEL<<<ggrid, gblock>>>(d[2 + (s & 1)], d[2 + ((s & 1) ^ 1)]);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    double out = -1.0;
+    if (e == cudaSuccess) {
+        drs_ref_maxdiff<<<1184, 256>>>(d[sweeps & 1], d[2 + (sweeps & 1)], n, res);
+        unsigned long long bits = 0;
+        if (cudaMemcpy(&bits, res, sizeof bits, cudaMemcpyDeviceToHost) == cudaSuccess) memcpy(&out, &bits, sizeof out);
+    }
+    cudaGetLastError();
+    for (int x = 0; x < 4; ++x) cudaFree(d[x]);
+    cudaFree(res);
+    return out;
 }
 
 // The emitted program, verbatim (prints the reference's own stdout lines).

@@ -219,9 +219,23 @@ def time_all(out_path):
                 lib = ctypes.CDLL(os.path.join(TUNE, c["so"]))
                 lib.drs_ref_time.restype = ctypes.c_float
                 lib.drs_ref_time.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                lib.drs_ref_check.restype = ctypes.c_double
+                lib.drs_ref_check.argtypes = [ctypes.c_int]
+                # the reference's own acceptance test first (--check: dr_ vs gold_, 1e-13 at its sizes; values stay
+                # below 2 after two sweeps of these operators, so 1e-12 absolute is the same bar with slack)
+                err = lib.drs_ref_check(2)
+                if not (0.0 <= err <= 1e-12):
+                    rows.append({"name": c["name"], "options": c["options"], "error": "fails its own --check (max |dr - gold| = %g)" % err
+                                 if err >= 0 else "launch failed (invalid launch shape on this GPU)"})
+                    print(wl, rows[-1], flush=True)
+                    continue
                 ms = min(lib.drs_ref_time(1, 20, 3) / 20 for _ in range(2))
-                rows.append({"name": c["name"], "options": c["options"], "ms_per_sweep": ms,
-                             "gstencil": pts * w["step"] / (ms * 1e-3) / 1e9 if ms > 0 else None})
+                if ms <= 0:
+                    rows.append({"name": c["name"], "options": c["options"], "error": "launch failed"})
+                    print(wl, rows[-1], flush=True)
+                    continue
+                rows.append({"name": c["name"], "options": c["options"], "ms_per_sweep": ms, "check_max_abs_error": err,
+                             "gstencil": pts * w["step"] / (ms * 1e-3) / 1e9})
             except Exception as e:
                 rows.append({"name": c["name"], "options": c["options"], "error": str(e)[:120]})
             print(wl, rows[-1], flush=True)

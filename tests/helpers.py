@@ -42,3 +42,15 @@ def max_rel(x, ref):
     ref = np.asarray(ref, dtype=np.float64)
     x = np.asarray(x, dtype=np.float64)
     return float(np.max(np.abs(x - ref)) / max(np.max(np.abs(ref)), 1e-300))
+
+
+def pointwise_rel(x, ref, floor_frac=1e-6):
+    """max over points of |x - ref| / max(|ref|, floor), floor = floor_frac * max |ref| (fields grow like
+    (sum of coefficients)^n and span many decades between the frozen ring and the centre; a global max-abs
+    measure alone says nothing about the small values)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    scale = float(np.max(np.abs(ref)))
+    if scale == 0.0:
+        return float(np.max(np.abs(x)))
+    return float(np.max(np.abs(x - ref) / np.maximum(np.abs(ref), floor_frac * scale)))

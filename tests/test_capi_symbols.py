@@ -34,3 +34,17 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cpp", ".hpp", ".cuh", ".h", ".cu")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_one_pinned_compiler_whatever_was_imported_first(built):
+    """Round 1: the library dlopen()ed "libnvrtc.so.12", which resolved to torch's copy (12.8) or the toolkit's (12.9)
+    depending on import order -- two compilers, two sets of cubins.  Now one absolute path is compiled in."""
+    import subprocess
+    import sys
+    import drstencil_b200 as drs
+    with_torch = drs.lib().drs_compiler().decode()
+    code = ("import ctypes, sys; assert 'torch' not in sys.modules; L = ctypes.CDLL(%r); "
+            "L.drs_compiler.restype = ctypes.c_char_p; print(L.drs_compiler().decode())"
+            % os.path.join(ROOT, "drstencil_b200", "libdrstencil.so"))
+    alone = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, text=True, check=True).stdout.strip()
+    assert alone == with_torch and alone.startswith("NVRTC ") and "(/" in alone

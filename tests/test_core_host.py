@@ -156,3 +156,36 @@ def test_no_gpu_means_loud_failure(built):
     with pytest.raises(drs.DrsError) as e:
         plan.sweep(ctypes.addressof(buf), ctypes.addressof(buf) + 8)
     assert e.value.code == drs.E_NOGPU
+
+
+def test_data_reuse_mode_plans_and_refusals(built):
+    """`--fuse reuse`: the plan carries the reference's partition as three ordered partial sums, and
+    refuses what the reference refuses, with its messages and the matching error codes."""
+    import pytest
+    import drstencil_b200 as drs
+    from helpers import stc_path
+
+    def plan(name, shape, **kn):
+        return drs.Plan(drs.Stencil.from_file(stc_path(name)).set_size(shape), drs.Knobs(fuse="reuse", **kn))
+
+    p = plan("2d5pt_star", (64, 64))
+    src = p.source
+    assert "drs_reuse.cuh" in src and "#define DRS_DIST 1" in src and "#define DRS_HAS_FWD_FAST 0" in src
+    # appendix B of SURVEY.md: out[j+1] = 0.2*in[j] + 0.3*in[j+1] (operands relative to the sweep centre j);
+    # backward = 0.2*in[j][i-1] + 0.2*in[j][i+1] + 0.2*in[j+1][i]
+    fwd = src[src.index("#define DRS_FWD_SLOW"):src.index("#define DRS_HAS_BWD")]
+    assert "MUL(0, 1, 0, 0.3)" in fwd and "FMA(0, 0, 0, 0.2)" in fwd and fwd.count("FMA(0") == 1
+    bwd = src[src.index("#define DRS_BWD"):src.index("#define DRS_HAS_FWD_MID")]
+    assert bwd.count("MUL(0") == 1 and bwd.count("FMA(0") == 2
+    p = plan("2d25pt_box", (64, 64))
+    assert "#define DRS_DIST 2" in p.source and "#define DRS_HAS_FWD_FAST 1" in p.source          # 15 / 4 / 6 (appendix C)
+    fast = p.source[p.source.index("#define DRS_FWD_FAST("):].split("#define")[1]
+    assert fast.count("MUL(0") + fast.count("FMA(0") == 6
+    p = plan("3d7pt_star", (32, 32, 32), step=2, merge_forward=1)
+    assert "#define DRS_HAS_FWD_MID 1" in p.source
+    with pytest.raises(drs.DrsError, match="No data to reuse") as e:
+        plan("2d5pt_cross", (64, 64))                       # drstencil_2d.hpp:217-220, exit 1
+    assert e.value.code == drs.E_NOREUSE
+    with pytest.raises(drs.DrsError, match="Invalid configuration") as e:
+        plan("2d25pt_box", (64, 64), bx=4)                  # codegen_2d.hpp:52-56
+    assert e.value.code == drs.E_CONFIG

@@ -5,7 +5,7 @@ Bars (BASELINE.json north_star): fp64 with the FMA order matched -> bit-exact; t
 import numpy as np
 import pytest
 
-from helpers import SHIPPED, max_rel, oracle_run, oracle_terms, stc_path
+from helpers import SHIPPED, max_rel, oracle_run, oracle_terms, pointwise_rel, stc_path
 
 pytestmark = pytest.mark.gpu
 
@@ -583,3 +583,95 @@ def test_run_as_cuda_graph_equals_plain_launches(built):
     g.replay()
     plan.sync_check()
     assert np.array_equal(A.cpu().numpy(), refA)
+
+
+@pytest.mark.parametrize("preset,timesteps,tol,ptol", [
+    ("c2", 128, 1e-12, 1e-11),     # 2d9pt_box fp64, temporal depth 4: bench.py's whole step (32 sweeps)
+    ("c3", 8, None, None),         # 2d25pt_box fp32, depth 1: bench.py's whole step (8 sweeps), bit-exact vs the fp32 oracle
+    ("c1", 10, None, None),        # 2d5pt_star fp64: 10 sweeps, bit-exact
+    ("c1t2", 20, 1e-12, 1e-11),
+])
+def test_whole_bench_schedules_against_the_oracle(built, preset, timesteps, tol, ptol):
+    """The schedules bench.py times (same knobs, same timesteps per step), on a 1024^2 grid the oracle finishes in
+    seconds: global AND floored pointwise relative error after the WHOLE schedule (temporal tests
+    stopped at 4 sweeps while the bench runs 32)."""
+    import drstencil_b200 as drs
+    from drstencil_b200.presets import PRESETS
+    from oracle import oracle
+    path, kn = PRESETS[preset]
+    shape = (1024, 1024)
+    st = drs.Stencil.from_file(path).set_size(shape)
+    plan = drs.Plan(st, kn)
+    f32 = kn.dtype == drs.F32
+    a64 = oracle.rand_array(shape)
+    a0 = a64.astype(np.float32) if f32 else a64
+    A, B = _dev(a0), _dev(np.zeros(shape, a0.dtype))
+    n = plan.run(A, B, timesteps)
+    plan.sync_check()
+    name = [s_ for s_ in SHIPPED if s_ in path][0]
+    assert n == drs.sweep_count(timesteps, kn.step)
+    got = A.cpu().numpy()
+    if tol is None:
+        ref, _ = oracle_run(name, kn.step, shape, n, a0.dtype, a0=a0)
+        assert np.array_equal(got, ref)
+        if f32:
+            ref64, _ = oracle_run(name, kn.step, shape, n, np.float64, a0=a64)
+            H = plan.halo
+            inner = (slice(H, -H), slice(H, -H))
+            assert max_rel(got[inner], ref64[inner]) <= 1e-5 and pointwise_rel(got[inner], ref64[inner]) <= 1e-4
+    else:
+        ref, _ = oracle_run(name, kn.step, shape, n, np.float64, a0=a64)
+        assert max_rel(got, ref) <= tol and pointwise_rel(got, ref) <= ptol, (max_rel(got, ref), pointwise_rel(got, ref))
+
+
+@pytest.mark.parametrize("preset,timesteps", [("c4", 16), ("c5", 10), ("c4t2", 16)])
+def test_whole_3d_bench_schedules_against_the_oracle(built, preset, timesteps):
+    import drstencil_b200 as drs
+    from drstencil_b200.presets import PRESETS
+    from oracle import oracle
+    path, kn = PRESETS[preset]
+    shape = (72, 200, 264)
+    st = drs.Stencil.from_file(path).set_size(shape)
+    plan = drs.Plan(st, kn)
+    a0 = oracle.rand_array(shape)
+    A, B = _dev(a0), _dev(np.zeros(shape))
+    n = plan.run(A, B, timesteps)
+    plan.sync_check()
+    ref, _ = oracle_run("3d7pt_star", kn.step, shape, n, a0=a0)
+    got = A.cpu().numpy()
+    if kn.step == 1:
+        assert np.array_equal(got, ref)
+    else:
+        assert max_rel(got, ref) <= 1e-12 and pointwise_rel(got, ref) <= 1e-11
+
+
+@pytest.mark.parametrize("name,shape,kn", [
+    ("2d5pt_star", (200, 264), dict()), ("2d9pt_star", (130, 150), dict()), ("2d9pt_box", (200, 265), dict(step=2)),
+    ("2d25pt_box", (150, 200), dict(bx=64, sn=7)), ("2d9pt_box", (120, 136), dict(step=4, merge_forward=30)),
+    ("2d5pt_cross", (100, 120), dict(step=2)), ("2d25pt_box", (130, 262), dict(dtype="f32")),
+    ("3d7pt_star", (40, 48, 72), dict()), ("3d7pt_star", (30, 41, 67), dict(step=2, merge_forward=1, bx=16, by=16, sn=5)),
+    ("3d9pt_cross", (30, 40, 64), dict(step=2)), ("3d7pt_star", (24, 40, 64), dict(dtype="f32", step=2)),
+])
+def test_data_reuse_mode_against_its_oracle(built, name, shape, kn):
+    """`--fuse reuse`: the reference's forward/backward evaluation as an A/B mode -- equal, bit for bit,
+    to the oracle's restatement of that scheme, within the reference's own bar of the gold expression, ring untouched."""
+    from oracle import oracle
+    plan = _plan(name, shape, fuse="reuse", **kn)
+    assert "drs_reuse.cuh" in plan.source and plan.info.kernel_name.startswith("dr_")
+    step = kn.get("step", 1)
+    f32 = kn.get("dtype") == "f32"
+    dt = np.float32 if f32 else np.float64
+    is3d = name.startswith("3d")
+    s = oracle.parse_stc(stc_path(name), is3d)
+    pts = oracle.compose(s.points, step)
+    a0 = oracle.rand_array(shape, dt)
+    A, B = _dev(a0), _dev(np.full(shape, -3.0, dt))
+    _sweeps(plan, A, B, 2)
+    ra, rb = a0.copy(), np.full(shape, -3.0, dt)
+    assert oracle.sweep_reuse(ra, rb, pts, s.dim, 0, kn.get("merge_forward", 5))
+    assert oracle.sweep_reuse(rb, ra, pts, s.dim, 0, kn.get("merge_forward", 5))
+    assert np.array_equal(B.cpu().numpy(), rb) and np.array_equal(A.cpu().numpy(), ra)
+    gold, _ = oracle_run(name, step, shape, 2, dt, a0=a0)
+    H = plan.info.halo
+    inner = tuple(slice(H, n - H) for n in shape)
+    assert max_rel(A.cpu().numpy()[inner], gold[inner]) <= (1e-5 if f32 else 1e-13)

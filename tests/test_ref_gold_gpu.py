@@ -69,6 +69,29 @@ def test_reference_gold_equals_oracle_equals_product(built, case):
         assert mx > 1e-3, "reference dr_ unexpectedly consistent for Dist > Halo"
     else:
         assert mx <= 1e-12, "reference dr_ vs its own gold: %g" % mx
+    # product in `--fuse reuse` mode (drs_reuse.cuh): the reference's own forward/backward evaluation -- against the
+    # reference's dr_ kernel itself, bit for bit wherever that kernel is deterministic (no cross-thread forward set),
+    # and against the oracle's restatement of the scheme
+    if dist <= halo:
+        st_r = drs.Stencil.from_file(os.path.join(ROOT, "stc", meta["stencil"] + ".stc")).set_size(shape, iters)
+        plan_r = drs.Plan(st_r, drs.Knobs(step=step, fuse="reuse", dist=dist))
+        A, B = torch.from_numpy(a0).cuda(), torch.zeros(shape, dtype=torch.float64, device="cuda")
+        assert plan_r.run(A, B, iters) == sweeps
+        plan_r.sync_check()
+        got = A.cpu().numpy()
+        s_ = oracle.parse_stc(os.path.join(ROOT, "stc", meta["stencil"] + ".stc"), meta["is3d"])
+        pts = oracle.compose(s_.points, step)
+        part = oracle.partition(pts, s_.dim, dist)
+        ra, rb = a0.copy(), np.zeros(shape)
+        bufs = [ra, rb]
+        for sw in range(sweeps):
+            assert oracle.sweep_reuse(bufs[sw & 1], bufs[(sw & 1) ^ 1], pts, s_.dim, dist)
+        assert np.array_equal(got, ra), "reuse mode != the oracle's restatement of the forward/backward scheme"
+        if not part["forward_mid"] and not part["forward_fast"]:
+            assert np.array_equal(got, da), "reuse mode != the reference's dr_ kernel"
+        else:
+            assert oracle.check_error(got, da, halo)[0] <= 1e-12       # the reference's atomics may land in either order
+        assert oracle.check_error(got, ga, halo)[0] <= 1e-12           # and its own acceptance bar against gold
     # product, literal composed operator -> bit-exact against the reference gold
     st = drs.Stencil.from_file(os.path.join(ROOT, "stc", meta["stencil"] + ".stc")).set_size(shape, iters)
     plan = drs.Plan(st, drs.Knobs(step=step, fuse="algebraic"))

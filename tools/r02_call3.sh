@@ -9,11 +9,11 @@ tail -4 $O/pytest_gpu.log
 t1=$(date +%s)
 timeout 900 python oracle/tune_ref.py time $O/ref_tune.json > $O/ref_tune.log 2>&1; echo "ref tune rc=$? seconds=$(( $(date +%s) - t1 ))" >> $O/ref_tune.log
 grep -E "^ref_tune|rc=" $O/ref_tune.log
-cd $O
+ROOT=$(pwd); cd $O
 tune() {  # name stc budget extra...
   local wl=$1 stc=$2 budget=$3; shift 3
   local t=$(date +%s)
-  timeout $(( budget * 2 + 400 )) python -m drstencil_b200.tuner.tune ../../stc/baseline/$stc --budget-s $budget --top 3 --ncu --min-seconds 0.5 \
+  PYTHONPATH=$ROOT timeout $(( budget * 2 + 400 )) python -m drstencil_b200.tuner.tune ../../stc/baseline/$stc --budget-s $budget --top 3 --ncu --min-seconds 0.5 \
       --out tune_$wl.json "$@" > tune_$wl.log 2>&1
   echo "tune $wl rc=$? seconds=$(( $(date +%s) - t ))"; grep WINNER tune_$wl.log
 }
