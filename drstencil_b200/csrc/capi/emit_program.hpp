@@ -96,35 +96,35 @@ static void gold_launch(const real_t* in, real_t* out) {
             o << "    dim3 grid(gx, (unsigned)nslow, 1);\n";
         o << "    DRS_NAME<<<grid, block>>>(p);\n}\n";
     } else if (s.tma_ok) {
-        o << "static CUtensorMap make_map(const real_t* base) {\n"
-             "    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,\n"
-             "        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,\n"
-             "        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);\n"
-             "    static encode_t encode = 0;\n"
-             "    if (!encode) { cudaDriverEntryPointQueryResult q; cudaFree(0);\n"
-             "        cudaGetDriverEntryPoint(\"cuTensorMapEncodeTiled\", (void**)&encode, cudaEnableDefault, &q);\n"
-             "        if (!encode) { printf(\"CUDA error : cuTensorMapEncodeTiled unavailable\\n\"); exit(-1); } }\n"
-             "    CUtensorMap m;\n";
-        o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
         if (s.flat) {
-            o << "    cuuint64_t dims[2] = {(cuuint64_t)GridL * GridM * GridN, 1};\n"
-                 "    cuuint64_t strides[1] = {(dims[0] * sizeof(real_t) + 15) / 16 * 16};\n";
-            o << "    cuuint32_t box[2] = {" << s.wb() << ", 1}; cuuint32_t es[2] = {1, 1};\n";
-            o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
-        } else if (s.dim == 2) {
-            o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
-            o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
-            o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            // row pitch not a multiple of 16 bytes: the kernels fill their ring with cp.async (DRS_FLAT) and ignore the map
+            o << "static CUtensorMap make_map(const real_t* base) { (void)base; CUtensorMap m; memset(&m, 0, sizeof m); return m; }\n";
         } else {
-            o << "    cuuint64_t dims[3] = {(cuuint64_t)GridN, (cuuint64_t)GridM, (cuuint64_t)GridL};\n"
-                 "    cuuint64_t strides[2] = {(cuuint64_t)GridN * sizeof(real_t), (cuuint64_t)GridN * GridM * sizeof(real_t)};\n";
-            o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.box_rows() << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
-            o << "    CUresult r = encode(&m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            o << "static CUtensorMap make_map(const real_t* base) {\n"
+                 "    typedef CUresult (*encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,\n"
+                 "        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,\n"
+                 "        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);\n"
+                 "    static encode_t encode = 0;\n"
+                 "    if (!encode) { cudaDriverEntryPointQueryResult q; cudaFree(0);\n"
+                 "        cudaGetDriverEntryPoint(\"cuTensorMapEncodeTiled\", (void**)&encode, cudaEnableDefault, &q);\n"
+                 "        if (!encode) { printf(\"CUDA error : cuTensorMapEncodeTiled unavailable\\n\"); exit(-1); } }\n"
+                 "    CUtensorMap m;\n";
+            o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
+            if (s.dim == 2) {
+                o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
+                o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
+                o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            } else {
+                o << "    cuuint64_t dims[3] = {(cuuint64_t)GridN, (cuuint64_t)GridM, (cuuint64_t)GridL};\n"
+                     "    cuuint64_t strides[2] = {(cuuint64_t)GridN * sizeof(real_t), (cuuint64_t)GridN * GridM * sizeof(real_t)};\n";
+                o << "    cuuint32_t box[3] = {" << s.wb() << ", " << s.box_rows() << ", 1}; cuuint32_t es[3] = {1, 1, 1};\n";
+                o << "    CUresult r = encode(&m, dt, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            }
+            o << "        CU_TENSOR_MAP_SWIZZLE_NONE, " << (s.dim == 3 ? "CU_TENSOR_MAP_L2_PROMOTION_L2_256B" : "CU_TENSOR_MAP_L2_PROMOTION_L2_128B")
+              << ", CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
+                 "    if (r != CUDA_SUCCESS) { printf(\"CUDA error : cuTensorMapEncodeTiled failed (%d)\\n\", (int)r); exit(-1); }\n"
+                 "    return m;\n}\n";
         }
-        o << "        CU_TENSOR_MAP_SWIZZLE_NONE, " << (s.dim == 3 ? "CU_TENSOR_MAP_L2_PROMOTION_L2_256B" : "CU_TENSOR_MAP_L2_PROMOTION_L2_128B")
-          << ", CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);\n"
-             "    if (r != CUDA_SUCCESS) { printf(\"CUDA error : cuTensorMapEncodeTiled failed (%d)\\n\", (int)r); exit(-1); }\n"
-             "    return m;\n}\n";
         o << "static void dr_launch_one(const real_t* in, real_t* out, int ring) {\n"
              "    static CUtensorMap maps[4]; static const real_t* bases[4] = {0, 0, 0, 0}; static int used = 0;\n"
              "    int b = 0;\n"

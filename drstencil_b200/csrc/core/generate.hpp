@@ -32,9 +32,8 @@ struct KernelSpec {
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
     int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
     bool tma_ok = true;         // false -> the naive kernel does the sweep (operator too deep, flat array too long)
-    // row pitch not a multiple of 16 bytes: no tiled tensor map exists; the array is described as one flat 1D
-    // tensor, a tile arrives as one TMA request per row, rows sit 128 bytes apart in shared memory and stores
-    // are scalar (drs_common.cuh: DRS_FLAT)
+    // row pitch not a multiple of 16 bytes: no tensor map can describe the array; the ring of stages is filled by
+    // the warp itself with element-sized cp.async and stores are scalar (drs_common.cuh: DRS_FLAT)
     bool flat = false;
     // 3D `--step n` in temporal mode: n launches of the single-step kernel with frozen rings of
     // r, 2r, ... n*r through plan-owned scratch buffers (sub-steps exactly as a fused kernel would
@@ -73,8 +72,7 @@ struct KernelSpec {
     int tile_rows() const { return fused3d ? nw * ry : ry; }
     int tile_rows_useful() const { return fused3d ? nw * ry - 2 * (ts - 1) * rj : ry; }
     int box_rows() const { return (share3d ? sy * ry : tile_rows()) + 2 * rj; }
-    int rp() const { return flat ? (wb() * esize() + 127) / 128 * 128 / esize() : wb(); }   // smem row pitch, elements
-    int stage_bytes() const { return dim == 2 ? rb * rp() * esize() : rp() * box_rows() * esize(); }
+    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * box_rows() * esize(); }
     int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
     int smem_bytes() const {
         if (fused3d) return (st + 2 * (ts - 1)) * stage_stride() + st * 8;
@@ -159,7 +157,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.flat = false;
         return "";
     }
-    s.flat = (st.N % vec) != 0;   // row pitch not a multiple of 16 bytes -> flat 1D tensor map (drs_common.cuh)
+    s.flat = (st.N % vec) != 0;   // row pitch not a multiple of 16 bytes -> cp.async ring, scalar stores (drs_common.cuh)
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
     if (temporal) {
         // The reference multiplies the operator out and prints the result with 6 significant digits
@@ -312,15 +310,6 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     while (s.smem_bytes() > 227 * 1024 && s.nw > 1 && !s.fused3d && !s.share3d) s.nw /= 2;
     while (s.smem_bytes() > 227 * 1024 && s.st > (s.dim == 3 ? pow2_ceil(2 * s.rk + 2) : 2)) s.st /= 2;
     s.tma_ok = true;
-    if (s.flat) {
-        // a flat coordinate is a 32-bit signed element index; the surplus iterations of a tile run a few planes /
-        // rows past the end of the array
-        const long double total = (long double)(s.dim == 3 ? st.L + 4 * (2 * s.halo + 2) : 1) * (long double)(st.M + 64) * (long double)st.N;
-        if (total >= 2147483647.0L) {
-            s.tma_ok = false;
-            s.note = "row pitch is not a multiple of 16 bytes and the array has more than 2^31 elements: naive kernel used";
-        }
-    }
     if (s.smem_bytes() > 227 * 1024) {
         // e.g. a radius-3 3D operator composed three times (radius 9: a ring of 32 planes): the reference still
         // emits a program for it, so the plan falls back to the naive one-thread-per-point kernel instead of failing

@@ -14,13 +14,14 @@
 #error "DRS_T (element type) must be defined by the generated translation unit"
 #endif
 
-// DRS_FLAT: the grid's row pitch is not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32), so no
-// tiled tensor map with row / plane strides exists.  The array is then described as ONE flat 1D tensor and a
-// tile arrives as one TMA request per row (a flat coordinate needs no alignment); rows are spaced 128 bytes
-// apart in shared memory (the destination of every request must be 128-byte aligned), and stores are scalar,
-// since rows start at alternating 16-byte offsets.  What the zero fill of the tiled map did at the ends of a
-// row is lost -- a box hanging over a row end reads the neighbouring row instead -- which is harmless: every
-// output whose cone leaves the grid lies in the frozen ring and is never stored.
+// DRS_FLAT: the grid's row pitch is not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32).  No tensor
+// map can describe such an array (strides must be multiples of 16 bytes) and a TMA box must start on a 16-byte
+// boundary, which every second row then misses.  The ring of shared-memory stages is kept -- same layout, same
+// mbarriers, same consumers -- but it is filled by the warp itself with element-sized cp.async (LDGSTS, zero fill
+// outside the grid exactly like the tensor map's) whose completion arrives on the stage's mbarrier
+// (cp.async.mbarrier.arrive.noinc, one arrival per lane); stores are scalar, since rows start at alternating
+// 16-byte offsets.  The reference's emitted kernels take any N through their i_ok guards
+// (/root/reference/codegen_2d.hpp:192-207); this is the engine's equivalent.
 #ifndef DRS_FLAT
 #define DRS_FLAT 0
 #endif
@@ -35,11 +36,6 @@ typedef DRS_T real;
 constexpr int kVec = 16 / (int)sizeof(real);  // elements per 128-bit access: 2 (f64) or 4 (f32)
 
 struct __align__(64) TensorMap { drs_u64 opaque[16]; };  // CUtensorMap, encoded on the host
-
-// row pitch of a staged tile in shared memory, in elements, for a TMA box WB elements wide
-__host__ __device__ constexpr int smem_row_pitch(int wb) {
-    return DRS_FLAT ? (int)(((wb * sizeof(real) + 127) / 128 * 128) / sizeof(real)) : wb;
-}
 
 // Kernel parameters common to the 2D and 3D sweeps (sizes are runtime values: unlike the
 // reference, which bakes L/M/N in as macros, one compiled plan serves any grid size).
@@ -205,12 +201,31 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
-// DRS_FLAT: the array as a {total, 1} tensor (rank 2 keeps the encoder's stride array non-empty); x = flat element index
-__device__ __forceinline__ void tma_load_1d(void* dst, const TensorMap* map, int x, drs_u64* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(0), "r"(smem_u32(bar))
-        : "memory");
+// DRS_FLAT: one element global -> shared, asynchronously; !valid writes a zero (what the tensor map's out-of-bounds
+// fill does).  cp_async_arrive makes this lane's earlier copies arrive on `bar` when they have landed.
+__device__ __forceinline__ void cp_async_elem(real* dst, const real* src, bool valid) {
+    const drs_u32 n = valid ? (drs_u32)sizeof(real) : 0u;
+    if constexpr (sizeof(real) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(drs_u64* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Rows [0, rows) x columns [0, wb) of a box whose corner is (y0, x0) of the plane at `plane` (row pitch N, M rows),
+// into shared memory at `dst` (row pitch wb): the share of lane `t` of `nt` cooperating threads.
+__device__ __forceinline__ void flat_fill(real* dst, const real* plane, bool plane_ok, drs_i64 M, drs_i64 N, int y0, int x0,
+                                          int rows, int wb, int t, int nt) {
+    for (int r = 0; r < rows; ++r) {
+        const drs_i64 y = (drs_i64)y0 + r;
+        const bool row_ok = plane_ok && y >= 0 && y < M;
+        const real* src = plane + y * N + x0;
+        for (int c = t; c < wb; c += nt) {
+            const bool ok = row_ok && x0 + c >= 0 && x0 + c < N;
+            cp_async_elem(dst + r * wb + c, ok ? src + c : plane, ok);
+        }
+    }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

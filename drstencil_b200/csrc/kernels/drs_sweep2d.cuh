@@ -59,7 +59,7 @@ constexpr int WT = 32 * C;          // columns a warp computes per row
 constexpr int WU = WT - 2 * HW;     // columns it stores
 constexpr int WB = WT + 2 * E0;     // TMA box width
 constexpr int ST = DRS_ST, RB = DRS_RB, NW = DRS_NW;
-constexpr int RP = smem_row_pitch(WB);   // row pitch inside a stage (== WB unless DRS_FLAT)
+constexpr int RP = WB;               // row pitch inside a stage
 constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);           // bytes the TMA unit delivers per stage
 constexpr int STAGE_STRIDE = (RB * RP * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
@@ -195,16 +195,16 @@ struct Stream {
     int x_box, yrow0;       // TMA coordinates: box column, level-0 row of iteration 0
     int NIT, NCH;           // input rows / stages this tile streams
     int lane;
-    drs_i64 N;              // row pitch of the grid (flat coordinates)
+    const real* in;         // DRS_FLAT: the warp fills its stages itself (cp.async), straight from the array
+    drs_i64 M, N;
+    // one stage = RB input rows; called by lane 0 (TMA) or by every lane of the warp (DRS_FLAT)
     __device__ __forceinline__ void issue(int c) const {
         const int s = c & (ST - 1);
-        mbar_expect_tx(&bars[s], STAGE_BYTES);
 #if DRS_FLAT
-#pragma unroll
-        for (int r = 0; r < RB; ++r)
-            tma_load_1d(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap,
-                        (int)((drs_i64)(yrow0 + c * RB + r) * N + x_box), &bars[s]);
+        flat_fill(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in, true, M, N, yrow0 + c * RB, x_box, RB, WB, lane, 32);
+        cp_async_arrive(&bars[s]);
 #else
+        mbar_expect_tx(&bars[s], STAGE_BYTES);
         tma_load_2d(wbase + s * STAGE_STRIDE, tmap, x_box, yrow0 + c * RB, &bars[s]);
 #endif
     }
@@ -224,10 +224,14 @@ __device__ __forceinline__ bool iteration(real (&w)[NLV][R2][SW], const Stream& 
     row_step<PH>(w, srow, t, n);
     if (rr == RB - 1) {
         __syncwarp();
+#if DRS_FLAT
+        if (c + ST < st.NCH) st.issue(c + ST);
+#else
         if (st.lane == 0 && c + ST < st.NCH) {
             fence_proxy_async();
             st.issue(c + ST);
         }
+#endif
     }
     return true;
 }
@@ -257,10 +261,12 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.tmap = &tmap;
     st.fault = p.fault;
     st.lane = lane;
+    st.in = p.in;
+    st.M = p.M;
     st.N = p.N;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], 1);
+        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT ? 32 : 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -294,7 +300,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.N = p.N;
     t.out = p.out;
 
-    if (lane == 0) {
+    if (DRS_FLAT || lane == 0) {
         for (int c = 0; c < ST && c < st.NCH; ++c) st.issue(c);
     }
 

@@ -41,7 +41,7 @@ constexpr int WB = WT + 2 * E0;       // box width
 constexpr int YB = RY + 2 * RJ;       // box height
 constexpr int ST = DRS_ST, NW = DRS_NW;
 constexpr int LA = ST - 2 * RK;       // planes requested ahead of the one being consumed
-constexpr int RP = smem_row_pitch(WB);   // row pitch inside a staged plane (== WB unless DRS_FLAT)
+constexpr int RP = WB;               // row pitch inside a staged plane
 constexpr int STAGE_BYTES = WB * YB * (int)sizeof(real);           // bytes the TMA unit delivers per plane
 constexpr int STAGE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
@@ -74,16 +74,17 @@ struct Stream {
     int x_box, y_box, z0;      // TMA coordinates of iteration 0
     int NIT;
     int lane;
-    drs_i64 M, N;              // grid pitches (flat coordinates)
+    const real* in;            // DRS_FLAT: the warp fills its stages itself (cp.async), straight from the array
+    drs_i64 L, M, N;
+    // one stage = one plane of the tile (+ halo); called by lane 0 (TMA) or by every lane of the warp (DRS_FLAT)
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
-        mbar_expect_tx(&bars[s], STAGE_BYTES);
 #if DRS_FLAT
-        const drs_i64 row0 = ((drs_i64)(z0 + n) * M + y_box) * N + x_box;
-#pragma unroll
-        for (int r = 0; r < YB; ++r)
-            tma_load_1d(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(row0 + r * N), &bars[s]);
+        const drs_i64 z = (drs_i64)z0 + n;
+        flat_fill(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, YB, WB, lane, 32);
+        cp_async_arrive(&bars[s]);
 #else
+        mbar_expect_tx(&bars[s], STAGE_BYTES);
         tma_load_3d(wbase + s * STAGE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
 #endif
     }
@@ -159,10 +160,14 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
     }
     // the oldest plane of the window is no longer needed: refill its stage
     __syncwarp();
+#if DRS_FLAT
+    if (n + LA < st.NIT) st.issue(n + LA);
+#else
     if (st.lane == 0 && n + LA < st.NIT) {
         fence_proxy_async();
         st.issue(n + LA);
     }
+#endif
     return true;
 }
 
@@ -195,11 +200,13 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.tmap = &tmap;
     st.fault = p.fault;
     st.lane = lane;
+    st.in = p.in;
+    st.L = p.L;
     st.M = p.M;
     st.N = p.N;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], 1);
+        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT ? 32 : 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -251,7 +258,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         }
     }
 
-    if (lane == 0) {
+    if (DRS_FLAT || lane == 0) {
         for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
     }
 

@@ -62,7 +62,7 @@ constexpr int HW = (((TS - 1) * E + kVec - 1) / kVec) * kVec;   // columns lost 
 constexpr int HY = (TS - 1) * RJ;                               // rows lost per side
 constexpr int WT = 32 * kVec, WU = WT - 2 * HW, WB = WT + 2 * E0;
 constexpr int TY = NW * RY, TYU = TY - 2 * HY, YB = TY + 2 * RJ;
-constexpr int RP = smem_row_pitch(WB);   // row pitch of every plane in shared memory (== WB unless DRS_FLAT)
+constexpr int RP = WB;               // row pitch of every plane in shared memory
 constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);           // bytes the TMA unit delivers per plane
 constexpr int PLANE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int NLV = TS - 1;                                     // intermediate levels kept in shared memory
@@ -94,15 +94,18 @@ struct Ctx {
     // slab mode: boundary output planes are also stored into the neighbours' ghost planes (NVLink)
     real* peer_lo; real* peer_hi;
     drs_i64 lo0, lo1, lo_shift, hi0, hi1, hi_shift;
+    const real* in;          // DRS_FLAT: the CTA fills its stages itself (cp.async), straight from the array
+    drs_i64 L;
+    // one stage = one plane of the tile (+ halo); called by thread 0 (TMA) or by every thread of the CTA (DRS_FLAT)
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
-        mbar_expect_tx(&bars[s], PLANE_BYTES);
 #if DRS_FLAT
-        const drs_i64 row0 = ((drs_i64)(z0 + n) * M + y_box) * N + x_box;
-#pragma unroll 4
-        for (int r = 0; r < YB; ++r)
-            tma_load_1d(ring + s * PLANE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(row0 + r * N), &bars[s]);
+        const drs_i64 z = (drs_i64)z0 + n;
+        flat_fill(reinterpret_cast<real*>(ring + s * PLANE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, YB, WB,
+                  (int)threadIdx.x, NW * 32);
+        cp_async_arrive(&bars[s]);
 #else
+        mbar_expect_tx(&bars[s], PLANE_BYTES);
         tma_load_3d(ring + s * PLANE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
 #endif
     }
@@ -244,10 +247,14 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
     }
     // published planes visible to every warp; the input stage is consumed by all of them
     __syncthreads();
+#if DRS_FLAT
+    if (n + ST < c.NIT) c.issue(n + ST);
+#else
     if (threadIdx.x == 0 && n + ST < c.NIT) {
         fence_proxy_async();
         c.issue(n + ST);
     }
+#endif
     return true;
 }
 
@@ -283,7 +290,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) mbar_init(&c.bars[s], 1);
+        for (int s = 0; s < ST; ++s) mbar_init(&c.bars[s], DRS_FLAT ? NW * 32 : 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -321,6 +328,8 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.z_out0 = za - DEPTH;
     c.M = p.M;
     c.N = p.N;
+    c.in = p.in;
+    c.L = p.L;
     c.out = p.out;
     c.peer_lo = p.peer_lo;
     c.peer_hi = p.peer_hi;
@@ -329,6 +338,19 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
 
     // slab runs (drs_run_slab): the thread that requests the planes waits for the neighbour's previous sweep
     // (on failure nothing is requested and the CTA leaves through the fault check of its first wait)
+#if DRS_FLAT
+    {
+        if constexpr (SLAB) {       // every thread fills the ring: all of them wait for thread 0's verdict
+            int go = 1;
+            if (threadIdx.x == 0) {
+                const int face = slab_face(p, zc);
+                go = (!face || slab_wait(p, face & 1, face & 2)) ? 1 : 0;
+            }
+            if (!__syncthreads_and(go)) return;
+        }
+        for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
+    }
+#else
     if (threadIdx.x == 0) {
         bool go = true;
         if constexpr (SLAB) {
@@ -338,6 +360,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         if (go)
             for (int n = 0; n < ST && n < c.NIT; ++n) c.issue(n);
     }
+#endif
 
     real pw[TS][K2][RY][kVec];
 #pragma unroll

@@ -63,6 +63,18 @@ for _n in ("3d7pt_star", "3d9pt_cross"):
     CASES["ship_" + _n] = (_n, True, (512, 512, 512), 4, 2, ["--bx", "32", "--by", "8", "--sn", "32"])
 
 
+# the winners of the reference's own search space on B200 (oracle/tune_ref.py; table: profiles/r02_ref_tune.json):
+# bench.py times these as `reference_gpu_kernels` instead of round 1's hand-picked options
+_BEST = os.path.join(HERE, "ref_best.json")
+_FULL = {"c1": ("2d5pt_star", False, (1, 4096, 4096), 10, 1), "c2": ("2d9pt_box", False, (1, 16384, 16384), 8, 4),
+         "c4": ("3d7pt_star", True, (768, 768, 768), 4, 1)}
+if os.path.exists(_BEST):
+    for _wl, _b in json.load(open(_BEST)).items():
+        if _wl in _FULL:
+            _stem, _is3d, _dims, _iters, _step = _FULL[_wl]
+            CASES["best_" + _wl] = (_stem, _is3d, _dims, _iters, _step, list(_b["options"]))
+
+
 def sh(cmd, **kw):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
     return r.returncode, r.stdout

@@ -4,11 +4,13 @@
 O=gpurun_out/r02_call3
 mkdir -p $O
 t0=$(date +%s)
-timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$? seconds=$(( $(date +%s) - t0 ))" >> $O/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$? seconds=$(( $(date +%s) - t0 ))" >> $O/pytest_gpu.log
 tail -4 $O/pytest_gpu.log
+if [ -n "$REF_TUNE" ]; then
 t1=$(date +%s)
 timeout 900 python oracle/tune_ref.py time $O/ref_tune.json > $O/ref_tune.log 2>&1; echo "ref tune rc=$? seconds=$(( $(date +%s) - t1 ))" >> $O/ref_tune.log
 grep -E "^ref_tune|rc=" $O/ref_tune.log
+fi
 ROOT=$(pwd); cd $O
 tune() {  # name stc budget extra...
   local wl=$1 stc=$2 budget=$3; shift 3
