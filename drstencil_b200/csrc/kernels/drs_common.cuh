@@ -213,17 +213,42 @@ __device__ __forceinline__ void cp_async_elem(real* dst, const real* src, bool v
 __device__ __forceinline__ void cp_async_arrive(drs_u64* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Rows [0, rows) x columns [0, wb) of a box whose corner is (y0, x0) of the plane at `plane` (row pitch N, M rows),
-// into shared memory at `dst` (row pitch wb): the share of lane `t` of `nt` cooperating threads.
-__device__ __forceinline__ void flat_fill(real* dst, const real* plane, bool plane_ok, drs_i64 M, drs_i64 N, int y0, int x0,
-                                          int rows, int wb, int t, int nt) {
-    for (int r = 0; r < rows; ++r) {
-        const drs_i64 y = (drs_i64)y0 + r;
-        const bool row_ok = plane_ok && y >= 0 && y < M;
-        const real* src = plane + y * N + x0;
-        for (int c = t; c < wb; c += nt) {
-            const bool ok = row_ok && x0 + c >= 0 && x0 + c < N;
-            cp_async_elem(dst + r * wb + c, ok ? src + c : plane, ok);
+// Rows [0, ROWS) x columns [0, WBX) of a box whose corner is (y0, x0) of the plane at `plane` (row pitch N, M rows),
+// into shared memory at `dst` (row pitch WBX): the share of thread `t` of NT cooperating threads.  A warp (NT <= WBX)
+// goes row by row, thread t taking columns t, t + NT, ... (column validity is the same for every row and is
+// computed once); a whole CTA (NT > WBX) walks the box as one run of ROWS*WBX elements.
+template <int ROWS, int WBX, int NT>
+__device__ __forceinline__ void flat_fill(real* dst, const real* plane, bool plane_ok, drs_i64 M, drs_i64 N, int y0, int x0, int t) {
+    if constexpr (NT <= WBX) {
+        constexpr int KC = (WBX + NT - 1) / NT;
+        bool cok[KC];
+#pragma unroll
+        for (int j = 0; j < KC; ++j) cok[j] = x0 + t + j * NT >= 0 && x0 + t + j * NT < N;
+        const real* src = plane + (drs_i64)y0 * N + x0 + t;
+        real* d = dst + t;
+#pragma unroll 2
+        for (int r = 0; r < ROWS; ++r) {
+            const bool row_ok = plane_ok && y0 + r >= 0 && y0 + r < M;
+#pragma unroll
+            for (int j = 0; j < KC; ++j) {
+                if (KC * NT <= WBX || t + j * NT < WBX) {
+                    const bool ok = row_ok && cok[j];
+                    cp_async_elem(d + j * NT, ok ? src + j * NT : plane, ok);
+                }
+            }
+            src += N;
+            d += WBX;
+        }
+    } else {
+        constexpr int TOTAL = ROWS * WBX, DR = NT / WBX, DC = NT % WBX;
+        int r = t / WBX, c = t % WBX;
+        const real* src = plane + ((drs_i64)y0 + r) * N + x0 + c;
+#pragma unroll 2
+        for (int q = t; q < TOTAL; q += NT) {
+            const bool ok = plane_ok && y0 + r >= 0 && y0 + r < M && x0 + c >= 0 && x0 + c < N;
+            cp_async_elem(dst + q, ok ? src : plane, ok);
+            c += DC; r += DR; src += (drs_i64)DR * N + DC;
+            if (c >= WBX) { c -= WBX; r += 1; src += N - WBX; }
         }
     }
 }

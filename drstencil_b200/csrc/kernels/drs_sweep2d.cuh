@@ -201,7 +201,7 @@ struct Stream {
     __device__ __forceinline__ void issue(int c) const {
         const int s = c & (ST - 1);
 #if DRS_FLAT
-        flat_fill(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in, true, M, N, yrow0 + c * RB, x_box, RB, WB, lane, 32);
+        flat_fill<RB, WB, 32>(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in, true, M, N, yrow0 + c * RB, x_box, lane);
         cp_async_arrive(&bars[s]);
 #else
         mbar_expect_tx(&bars[s], STAGE_BYTES);

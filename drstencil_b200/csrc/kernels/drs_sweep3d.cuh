@@ -81,7 +81,7 @@ struct Stream {
         const int s = n & (ST - 1);
 #if DRS_FLAT
         const drs_i64 z = (drs_i64)z0 + n;
-        flat_fill(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, YB, WB, lane, 32);
+        flat_fill<YB, WB, 32>(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, lane);
         cp_async_arrive(&bars[s]);
 #else
         mbar_expect_tx(&bars[s], STAGE_BYTES);

@@ -101,8 +101,8 @@ struct Ctx {
         const int s = n & (ST - 1);
 #if DRS_FLAT
         const drs_i64 z = (drs_i64)z0 + n;
-        flat_fill(reinterpret_cast<real*>(ring + s * PLANE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, YB, WB,
-                  (int)threadIdx.x, NW * 32);
+        flat_fill<YB, WB, NW * 32>(reinterpret_cast<real*>(ring + s * PLANE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box,
+                                   (int)threadIdx.x);
         cp_async_arrive(&bars[s]);
 #else
         mbar_expect_tx(&bars[s], PLANE_BYTES);

@@ -20,12 +20,12 @@ def _p(*parts):
 
 # workload -> (stc file, dimensionality, configuration name == winners[0].name of profiles/r02_tune_<workload>.json)
 TUNED = {
-    "c1": (_p("baseline", "c1_2d5pt_star.stc"), 2, "fu1d0bx64sn128u4bmx2mf5st2"),
-    "c2": (_p("baseline", "c2_2d9pt_box.stc"), 2, "fu4d0bx64sn256u4bmx2mf5st2"),
-    "c3": (_p("baseline", "c3_2d25pt_box.stc"), 2, "fu1d0bx64sn32u8bmx1mf5st2mb4f32"),
-    "c4": (_p("baseline", "c4_3d7pt_star.stc"), 3, "fu1d0bx32y2sn16u4bmx1bmy1mf5ry4"),
-    # four warps (2 x 2) sharing one input ring per CTA, eight rows per thread: 386.6 vs 376.8 GStencil/s sustained
-    # for round 1's private rings (profiles/r02_c5_shared_ring_probe.txt)
+    "c1": (_p("baseline", "c1_2d5pt_star.stc"), 2, "fu1d0bx32sn128u4bmx2mf5st2"),
+    "c2": (_p("baseline", "c2_2d9pt_box.stc"), 2, "fu4d0bx128sn256u4bmx2mf5st2"),
+    "c3": (_p("baseline", "c3_2d25pt_box.stc"), 2, "fu1d0bx64sn32u8bmx1mf5st2f32"),
+    # c4 / c5: four warps (2 x 2) share one input ring per CTA (drs_sweep3d_cta.cuh); c5 with eight rows per thread
+    # (9.32 ms sustained vs 9.50 for round 1's private rings with six rows)
+    "c4": (_p("baseline", "c4_3d7pt_star.stc"), 3, "fu1d0bx32y4sn64u4bmx1bmy1mf5ry4sx2sy2"),
     "c5": (_p("baseline", "c5_3d7pt_star.stc"), 3, "fu1d0bx32y4sn64u4bmx1bmy1mf5ry8sx2sy2"),
 }
 

@@ -85,3 +85,28 @@ def test_ncu_parser_by_name():
     assert 4.2e9 < s["dram_bytes"] < 4.6e9                      # ~ the 4.29 GB algorithmic bytes
     assert 3000 < s["dram_gbs"] < 3600
     assert s["launch__registers_per_thread"] == 130
+
+
+def test_every_baseline_preset_is_a_tuner_winner_with_its_ncu_evidence():
+    """SURVEY 8f-1 / BASELINE north_star: every chosen configuration is justified by ncu-measured DRAM GB/s and L2 /
+    shared-memory traffic.  Each BASELINE preset must be the winner of its committed tuner record
+    (profiles/r02_tune_<workload>.json: sustained timing, Nsight Compute by metric name)."""
+    import json
+    from drstencil_b200.presets import TUNED
+    for wl, (path, dim, name) in TUNED.items():
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r02_tune_%s.json" % wl)))
+        assert rec["stencil"] == os.path.basename(path) and rec["min_seconds_per_candidate"] >= 0.5
+        w = rec["winners"][0]
+        assert w["name"] == name, (wl, w["name"], name)
+        assert w["ms_confirmed"] <= min(x["ms_confirmed"] for x in rec["winners"]) + 1e-12
+        assert w["sweeps_confirmed"] * w["ms_confirmed"] >= 900          # >= 0.9 s of back-to-back sweeps
+        ncu = w["ncu"]
+        assert "error" not in ncu and ncu["launches"] >= 2
+        for key in ("dram_gbs", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+                    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "gpu__time_duration.sum"):
+            assert ncu.get(key, 0) > 0, (wl, key)
+        assert 3000 < ncu["dram_gbs"] < 8000
+        # the record holds the whole search: the space, a burst figure for every configuration, sustained figures
+        # for the finalists
+        assert rec["tried"] == rec["space"] == len(rec["all"])
+        assert sum(1 for r in rec["all"] if r.get("ms") is not None) >= rec["space"] // 4
