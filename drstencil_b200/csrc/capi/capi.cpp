@@ -369,7 +369,7 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     auto it = p->tmaps.find(base);
     if (it != p->tmaps.end()) { *out = &it->second; return DRS_OK; }
     const drs::KernelSpec& s = p->spec;
-    if (!s.flat && (reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
+    if (s.flat != 2 && (reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(DRS_E_ARG, "device buffers must be 16-byte aligned");
     CUtensorMap m;
     const CUtensorMapDataType dt = s.dtype == DRS_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const cuuint64_t es = (cuuint64_t)s.esize();
@@ -378,11 +378,21 @@ int tensor_map_for(drs_plan* p, const void* base, CUtensorMap** out) {
     // 128 B are equal), 128 B for row boxes (2D: no difference).  DRS_TMA_L2PROMO=0..3 overrides (development aid).
     CUtensorMapL2promotion promo = s.dim == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (const char* e = getenv("DRS_TMA_L2PROMO")) promo = (CUtensorMapL2promotion)atoi(e);
-    if (s.flat) {
-        // no tensor map exists for this row pitch and the kernel does not use one (DRS_FLAT): the parameter slot
-        // carries zeros
+    if (s.flat == 2) {
+        // the kernel fills its stages with cp.async and uses no tensor map: the parameter slot carries zeros
         std::memset(&m, 0, sizeof m);
         r = CUDA_SUCCESS;
+    } else if (s.flat == 1) {
+        // the whole array as one row of a {total, 1} tensor; a tile arrives as one box of wb() + vec() elements per row,
+        // each starting on a 16-byte boundary (a rank-1 map is not an option: the encoder wants a stride array)
+        const cuuint64_t total = (cuuint64_t)p->st.L * (cuuint64_t)p->st.M * (cuuint64_t)p->st.N;
+        cuuint64_t dims[2] = {total, 1};
+        cuuint64_t strides[1] = {(total * es + 15) / 16 * 16};
+        cuuint32_t box[2] = {(cuuint32_t)(s.wb() + s.vec()), 1};
+        cuuint32_t estr[2] = {1, 1};
+        r = driver().TensorMapEncodeTiled(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else if (s.dim == 2) {
         cuuint64_t dims[2] = {(cuuint64_t)p->st.N, (cuuint64_t)p->st.M};
         cuuint64_t strides[1] = {(cuuint64_t)p->st.N * es};

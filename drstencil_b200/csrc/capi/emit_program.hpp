@@ -96,8 +96,8 @@ static void gold_launch(const real_t* in, real_t* out) {
             o << "    dim3 grid(gx, (unsigned)nslow, 1);\n";
         o << "    DRS_NAME<<<grid, block>>>(p);\n}\n";
     } else if (s.tma_ok) {
-        if (s.flat) {
-            // row pitch not a multiple of 16 bytes: the kernels fill their ring with cp.async (DRS_FLAT) and ignore the map
+        if (s.flat == 2) {
+            // row pitch not a multiple of 16 bytes, cp.async ring (DRS_FLAT 2): the kernel ignores the map
             o << "static CUtensorMap make_map(const real_t* base) { (void)base; CUtensorMap m; memset(&m, 0, sizeof m); return m; }\n";
         } else {
             o << "static CUtensorMap make_map(const real_t* base) {\n"
@@ -110,7 +110,13 @@ static void gold_launch(const real_t* in, real_t* out) {
                  "        if (!encode) { printf(\"CUDA error : cuTensorMapEncodeTiled unavailable\\n\"); exit(-1); } }\n"
                  "    CUtensorMap m;\n";
             o << "    const CUtensorMapDataType dt = " << (s.dtype == DRS_F64 ? "CU_TENSOR_MAP_DATA_TYPE_FLOAT64" : "CU_TENSOR_MAP_DATA_TYPE_FLOAT32") << ";\n";
-            if (s.dim == 2) {
+            if (s.flat == 1) {
+                // row pitch not a multiple of 16 bytes, per-row TMA (DRS_FLAT 1): the array as one row of a {total, 1} tensor
+                o << "    cuuint64_t dims[2] = {(cuuint64_t)GridL * GridM * GridN, 1};\n"
+                     "    cuuint64_t strides[1] = {(dims[0] * sizeof(real_t) + 15) / 16 * 16};\n";
+                o << "    cuuint32_t box[2] = {" << s.wb() + s.vec() << ", 1}; cuuint32_t es[2] = {1, 1};\n";
+                o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";
+            } else if (s.dim == 2) {
                 o << "    cuuint64_t dims[2] = {(cuuint64_t)GridN, (cuuint64_t)GridM}; cuuint64_t strides[1] = {(cuuint64_t)GridN * sizeof(real_t)};\n";
                 o << "    cuuint32_t box[2] = {" << s.wb() << ", " << s.rb << "}; cuuint32_t es[2] = {1, 1};\n";
                 o << "    CUresult r = encode(&m, dt, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,\n";

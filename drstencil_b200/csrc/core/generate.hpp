@@ -32,9 +32,10 @@ struct KernelSpec {
     // geometry (see drs_sweep2d.cuh / drs_sweep3d.cuh)
     int nw = 2, st = 4, rb = 4, ry = 8, vt = 1, minb = 1, chunk = 128;
     bool tma_ok = true;         // false -> the naive kernel does the sweep (operator too deep, flat array too long)
-    // row pitch not a multiple of 16 bytes: no tensor map can describe the array; the ring of stages is filled by
-    // the warp itself with element-sized cp.async and stores are scalar (drs_common.cuh: DRS_FLAT)
-    bool flat = false;
+    // row pitch not a multiple of 16 bytes (drs_common.cuh: DRS_FLAT): 1 = one TMA request per row of a tile from a
+    // {total, 1} tensor map, consumers add the row's shift; 2 = the warp fills the stages itself with cp.async
+    // (arrays of 2^31 elements or more, the fused 3D temporal kernel).  Scalar stores in both.
+    int flat = 0;
     // 3D `--step n` in temporal mode: n launches of the single-step kernel with frozen rings of
     // r, 2r, ... n*r through plan-owned scratch buffers (sub-steps exactly as a fused kernel would
     // evaluate them; not yet fused in one kernel -- no HBM saving, but no 25/35-point operator either)
@@ -72,7 +73,8 @@ struct KernelSpec {
     int tile_rows() const { return fused3d ? nw * ry : ry; }
     int tile_rows_useful() const { return fused3d ? nw * ry - 2 * (ts - 1) * rj : ry; }
     int box_rows() const { return (share3d ? sy * ry : tile_rows()) + 2 * rj; }
-    int stage_bytes() const { return dim == 2 ? rb * wb() * esize() : wb() * box_rows() * esize(); }
+    int rp() const { return flat == 1 ? ((wb() + vec()) * esize() + 127) / 128 * 128 / esize() : wb(); }   // smem row pitch, elements
+    int stage_bytes() const { return dim == 2 ? rb * rp() * esize() : rp() * box_rows() * esize(); }
     int stage_stride() const { return (stage_bytes() + 127) / 128 * 128; }
     int smem_bytes() const {
         if (fused3d) return (st + 2 * (ts - 1)) * stage_stride() + st * 8;
@@ -157,7 +159,14 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.flat = false;
         return "";
     }
-    s.flat = (st.N % vec) != 0;   // row pitch not a multiple of 16 bytes -> cp.async ring, scalar stores (drs_common.cuh)
+    if ((st.N % vec) != 0) {      // row pitch not a multiple of 16 bytes (drs_common.cuh: DRS_FLAT)
+        // per-row TMA needs flat element indices in a signed 32-bit coordinate; the surplus iterations of a tile run
+        // a few rows / planes past the end of the array
+        const long double total = (long double)(s.dim == 3 ? st.L + 64 : 1) * (long double)(st.M + 256) * (long double)st.N;
+        s.flat = total < 2147483647.0L ? 1 : 2;
+        // development aid / tests: DRS_FLAT_MODE=2 forces the cp.async form on small grids too
+        if (const char* e = std::getenv("DRS_FLAT_MODE")) if (std::atoi(e) == 2) s.flat = 2;
+    }
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
     if (temporal) {
         // The reference multiplies the operator out and prints the result with 6 significant digits
@@ -207,7 +216,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
     }
     s.base_order = order;
     if (temporal) { s.ts = k.step; s.chain = st.base_terms(); }
-    else if (fused3d) { s.ts = k.step; s.chain = st.base_terms(); s.fused3d = true; }
+    else if (fused3d) { s.ts = k.step; s.chain = st.base_terms(); s.fused3d = true; if (s.flat) s.flat = 2; }
     else if (multi3d) { s.ts = 1; s.chain = st.base_terms(); s.sub_launches = k.step; }
     else { s.ts = 1; s.chain = s.gold; s.fuse = k.step > 1 ? DRS_FUSE_ALGEBRAIC : k.fuse; }
     s.rk = s.rj = s.e = 0;
@@ -492,7 +501,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     o << "#define DRS_NW " << s.nw << "\n#define DRS_ST " << s.st << "\n#define DRS_RB " << s.rb << "\n";
     o << "#define DRS_RY " << s.ry << "\n#define DRS_VT " << s.vt << "\n#define DRS_MINB " << s.minb << "\n";
     if (s.share3d) o << "#define DRS_SX " << s.sx << "\n#define DRS_SY " << s.sy << "\n";
-    if (s.flat) o << "#define DRS_FLAT 1\n";
+    if (s.flat) o << "#define DRS_FLAT " << s.flat << "\n";
     // development aid: DRS_EXTRA_DEFINES="A=1;B=2" adds `#define A 1` ... to the translation unit
     // (tools/probe_shape.py experiments; part of the source, hence of the cubin cache key)
     if (const char* xd = std::getenv("DRS_EXTRA_DEFINES")) {

@@ -14,13 +14,22 @@
 #error "DRS_T (element type) must be defined by the generated translation unit"
 #endif
 
-// DRS_FLAT: the grid's row pitch is not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32).  No tensor
-// map can describe such an array (strides must be multiples of 16 bytes) and a TMA box must start on a 16-byte
-// boundary, which every second row then misses.  The ring of shared-memory stages is kept -- same layout, same
-// mbarriers, same consumers -- but it is filled by the warp itself with element-sized cp.async (LDGSTS, zero fill
-// outside the grid exactly like the tensor map's) whose completion arrives on the stage's mbarrier
-// (cp.async.mbarrier.arrive.noinc, one arrival per lane); stores are scalar, since rows start at alternating
-// 16-byte offsets.  The reference's emitted kernels take any N through their i_ok guards
+// DRS_FLAT != 0: the grid's row pitch is not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32).  No
+// tensor map can describe such an array by rows (strides must be multiples of 16 bytes), and a TMA box must START on
+// a 16-byte boundary (measured: tools/tma_align_probe.cu), which every second row of an odd-N fp64 grid misses.  The
+// ring of shared-memory stages is kept -- same mbarriers, same consumers, same chain -- and filled in one of two ways:
+//   DRS_FLAT == 1  the array is described as ONE row of a {total, 1} tensor and a tile arrives as one TMA request per
+//                  ROW, each starting at the 16-byte boundary at or below the row's first element; the row's data then
+//                  sits `shift` (0 .. kVec-1) elements into its slot, and the consumers add that shift (their 128-bit
+//                  shared loads become scalar ones).  Rows are 128 bytes apart in shared memory (a TMA destination
+//                  must be 128-byte aligned).  A flat coordinate is a signed 32-bit element index: arrays below 2^31
+//                  elements only.
+//   DRS_FLAT == 2  (larger arrays, and the fused 3D temporal kernel) the warp fills the stages itself with
+//                  element-sized cp.async (LDGSTS, zero fill outside the grid) whose completion arrives on the stage's
+//                  mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per lane); layout as in the aligned case.
+// Stores are scalar in both, since rows start at alternating 16-byte offsets.  With DRS_FLAT == 1 a box that hangs
+// over a row end reads the neighbouring row instead of zeros -- harmless: every output whose cone leaves the grid
+// lies in the frozen ring and is never stored.  The reference's emitted kernels take any N through their i_ok guards
 // (/root/reference/codegen_2d.hpp:192-207); this is the engine's equivalent.
 #ifndef DRS_FLAT
 #define DRS_FLAT 0
@@ -36,6 +45,14 @@ typedef DRS_T real;
 constexpr int kVec = 16 / (int)sizeof(real);  // elements per 128-bit access: 2 (f64) or 4 (f32)
 
 struct __align__(64) TensorMap { drs_u64 opaque[16]; };  // CUtensorMap, encoded on the host
+
+// DRS_FLAT == 1: width of the per-row TMA box (the tile's box plus room for the shift) and the row pitch of a stage
+__host__ __device__ constexpr int flat_box(int wb) { return wb + kVec; }
+__host__ __device__ constexpr int smem_row_pitch(int wb) {
+    return DRS_FLAT == 1 ? (int)(((flat_box(wb) * sizeof(real) + 127) / 128 * 128) / sizeof(real)) : wb;
+}
+// elements between the 16-byte boundary at or below flat element index f and f itself
+__host__ __device__ constexpr int flat_shift(drs_i64 f) { return (int)(f & (drs_i64)(kVec - 1)); }
 
 // Kernel parameters common to the 2D and 3D sweeps (sizes are runtime values: unlike the
 // reference, which bakes L/M/N in as macros, one compiled plan serves any grid size).
@@ -201,7 +218,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
 }
-// DRS_FLAT: one element global -> shared, asynchronously; !valid writes a zero (what the tensor map's out-of-bounds
+// DRS_FLAT == 1: one row of a tile; x = flat element index of the box start (a multiple of kVec)
+__device__ __forceinline__ void tma_load_row(void* dst, const TensorMap* map, int x, drs_u64* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(0), "r"(smem_u32(bar))
+        : "memory");
+}
+// DRS_FLAT == 2: one element global -> shared, asynchronously; !valid writes a zero (what the tensor map's out-of-bounds
 // fill does).  cp_async_arrive makes this lane's earlier copies arrive on `bar` when they have landed.
 __device__ __forceinline__ void cp_async_elem(real* dst, const real* src, bool valid) {
     const drs_u32 n = valid ? (drs_u32)sizeof(real) : 0u;
@@ -267,6 +291,14 @@ __device__ __forceinline__ float rfma(float a, float b, float c) { return __fmaf
 
 // 128-bit shared loads / global stores of kVec elements
 __device__ __forceinline__ void lds_vec(real (&v)[kVec], const real* p) {
+    if constexpr (DRS_FLAT == 1) {
+        // the row's shift (warp-uniform) may break the 16-byte alignment of the vector: scalar loads then
+        if ((smem_u32(p) & 15u) != 0u) {
+#pragma unroll
+            for (int x = 0; x < kVec; ++x) v[x] = p[x];
+            return;
+        }
+    }
     if constexpr (sizeof(real) == 8) {
         double2 t = *reinterpret_cast<const double2*>(p);
         v[0] = t.x; v[1] = t.y;
@@ -276,10 +308,15 @@ __device__ __forceinline__ void lds_vec(real (&v)[kVec], const real* p) {
     }
 }
 __device__ __forceinline__ void stg_vec(real* p, const real (&v)[kVec]) {
-    if constexpr (DRS_FLAT != 0) {          // rows start at any element: no 16-byte alignment to rely on
+    if constexpr (DRS_FLAT != 0) {
+        // rows start at any element: whether this row's vectors are 16-byte aligned is a (warp-uniform) run-time fact
+        if ((reinterpret_cast<drs_u64>(p) & 15ull) != 0ull) {
 #pragma unroll
-        for (int x = 0; x < kVec; ++x) p[x] = v[x];
-    } else if constexpr (sizeof(real) == 8) {
+            for (int x = 0; x < kVec; ++x) p[x] = v[x];
+            return;
+        }
+    }
+    if constexpr (sizeof(real) == 8) {
         *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     } else {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);

@@ -59,8 +59,8 @@ constexpr int WT = 32 * C;          // columns a warp computes per row
 constexpr int WU = WT - 2 * HW;     // columns it stores
 constexpr int WB = WT + 2 * E0;     // TMA box width
 constexpr int ST = DRS_ST, RB = DRS_RB, NW = DRS_NW;
-constexpr int RP = WB;               // row pitch inside a stage
-constexpr int STAGE_BYTES = RB * WB * (int)sizeof(real);           // bytes the TMA unit delivers per stage
+constexpr int RP = smem_row_pitch(WB);   // row pitch inside a stage (== WB unless DRS_FLAT == 1)
+constexpr int STAGE_BYTES = RB * (DRS_FLAT == 1 ? flat_box(WB) : WB) * (int)sizeof(real);   // bytes the TMA unit delivers per stage
 constexpr int STAGE_STRIDE = (RB * RP * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
 // iterations between a row entering and the output that completes with it leaving
@@ -200,9 +200,17 @@ struct Stream {
     // one stage = RB input rows; called by lane 0 (TMA) or by every lane of the warp (DRS_FLAT)
     __device__ __forceinline__ void issue(int c) const {
         const int s = c & (ST - 1);
-#if DRS_FLAT
+#if DRS_FLAT == 2
         flat_fill<RB, WB, 32>(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in, true, M, N, yrow0 + c * RB, x_box, lane);
         cp_async_arrive(&bars[s]);
+#elif DRS_FLAT == 1
+        mbar_expect_tx(&bars[s], STAGE_BYTES);
+        const drs_i64 f0 = (drs_i64)(yrow0 + c * RB) * N + x_box;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const drs_i64 f = f0 + r * N;
+            tma_load_row(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(f - flat_shift(f)), &bars[s]);
+        }
 #else
         mbar_expect_tx(&bars[s], STAGE_BYTES);
         tma_load_2d(wbase + s * STAGE_STRIDE, tmap, x_box, yrow0 + c * RB, &bars[s]);
@@ -220,11 +228,16 @@ __device__ __forceinline__ bool iteration(real (&w)[NLV][R2][SW], const Stream& 
     if (rr == 0) {
         if (!mbar_wait(&st.bars[s], (drs_u32)((c / ST) & 1), st.fault)) return false;
     }
+#if DRS_FLAT == 1
+    const real* srow = reinterpret_cast<const real*>(st.wbase + s * STAGE_STRIDE) + rr * RP +
+                       flat_shift((drs_i64)(st.yrow0 + n) * st.N + st.x_box);
+#else
     const real* srow = reinterpret_cast<const real*>(st.wbase + s * STAGE_STRIDE) + rr * RP;
+#endif
     row_step<PH>(w, srow, t, n);
     if (rr == RB - 1) {
         __syncwarp();
-#if DRS_FLAT
+#if DRS_FLAT == 2
         if (c + ST < st.NCH) st.issue(c + ST);
 #else
         if (st.lane == 0 && c + ST < st.NCH) {
@@ -266,7 +279,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.N = p.N;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT ? 32 : 1);
+        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT == 2 ? 32 : 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -300,7 +313,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     t.N = p.N;
     t.out = p.out;
 
-    if (DRS_FLAT || lane == 0) {
+    if (DRS_FLAT == 2 || lane == 0) {
         for (int c = 0; c < ST && c < st.NCH; ++c) st.issue(c);
     }
 

@@ -41,8 +41,8 @@ constexpr int WB = WT + 2 * E0;       // box width
 constexpr int YB = RY + 2 * RJ;       // box height
 constexpr int ST = DRS_ST, NW = DRS_NW;
 constexpr int LA = ST - 2 * RK;       // planes requested ahead of the one being consumed
-constexpr int RP = WB;               // row pitch inside a staged plane
-constexpr int STAGE_BYTES = WB * YB * (int)sizeof(real);           // bytes the TMA unit delivers per plane
+constexpr int RP = smem_row_pitch(WB);   // row pitch inside a staged plane (== WB unless DRS_FLAT == 1)
+constexpr int STAGE_BYTES = (DRS_FLAT == 1 ? flat_box(WB) : WB) * YB * (int)sizeof(real);   // bytes the TMA unit delivers per plane
 constexpr int STAGE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int WARP_SMEM = ST * STAGE_STRIDE;
 static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
@@ -79,10 +79,18 @@ struct Stream {
     // one stage = one plane of the tile (+ halo); called by lane 0 (TMA) or by every lane of the warp (DRS_FLAT)
     __device__ __forceinline__ void issue(int n) const {
         const int s = n & (ST - 1);
-#if DRS_FLAT
+#if DRS_FLAT == 2
         const drs_i64 z = (drs_i64)z0 + n;
         flat_fill<YB, WB, 32>(reinterpret_cast<real*>(wbase + s * STAGE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box, lane);
         cp_async_arrive(&bars[s]);
+#elif DRS_FLAT == 1
+        mbar_expect_tx(&bars[s], STAGE_BYTES);
+        const drs_i64 f0 = flat0(n);
+#pragma unroll
+        for (int r = 0; r < YB; ++r) {
+            const drs_i64 f = f0 + r * N;
+            tma_load_row(wbase + s * STAGE_STRIDE + r * RP * (int)sizeof(real), tmap, (int)(f - flat_shift(f)), &bars[s]);
+        }
 #else
         mbar_expect_tx(&bars[s], STAGE_BYTES);
         tma_load_3d(wbase + s * STAGE_STRIDE, tmap, x_box, y_box, z0 + n, &bars[s]);
@@ -91,16 +99,29 @@ struct Stream {
     __device__ __forceinline__ const real* plane(int n) const {
         return reinterpret_cast<const real*>(wbase + (n & (ST - 1)) * STAGE_STRIDE);
     }
+    // DRS_FLAT == 1: flat element index of the first element of box row 0 of plane n; box row r of that plane sits
+    // flat_shift(flat0(n) + r * N) elements into its slot
+    __device__ __forceinline__ drs_i64 flat0(int n) const { return (((drs_i64)z0 + n) * M + y_box) * N + x_box; }
 };
 
 template <int PH>
 __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream& st, const Tile& t, int n) {
     if (!mbar_wait(&st.bars[n & (ST - 1)], (drs_u32)((n / ST) & 1), st.fault)) return false;
+#if DRS_FLAT == 1
+    // row (y + RJ) of window plane d holds its data DRS_SH_(d, y) elements into its slot
+    int fl[K2];                                           // shift of box row 0 of each window plane
+#pragma unroll
+    for (int d = 0; d < K2; ++d) fl[d] = flat_shift(st.flat0(n - 2 * RK + d));
+    const int nm = (int)(st.N & (drs_i64)(kVec - 1));     // the shift advances by N mod kVec per row
+#define DRS_SH_(d, yy) ((fl[d] + ((yy) + RJ) * nm) & (kVec - 1))
+#else
+#define DRS_SH_(d, yy) 0
+#endif
     // newest plane: own vectors of every tile row into the queue
     {
         const real* pl = st.plane(n) + RJ * RP + E0 + t.lane * kVec;
 #pragma unroll
-        for (int y = 0; y < RY; ++y) lds_vec(q[PH][y], pl + y * RP);
+        for (int y = 0; y < RY; ++y) lds_vec(q[PH][y], pl + y * RP + DRS_SH_(K2 - 1, y));
     }
     if (n >= t.n_first && n < t.n_end) {
         // staged planes of the window: sp[dk + RK] -> this thread's element 0 of tile row 0
@@ -125,12 +146,12 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
 #define DRS_OPERAND_(dk, dj, di)                                                               \
     (((v + (di)) >= 0 && (v + (di)) < kVec && (y + (dj)) >= 0 && (y + (dj)) < RY)              \
          ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][clampi(v + (di), 0, kVec - 1)]         \
-         : sp[(dk) + RK][(y + (dj)) * RP + v + (di)])
+         : sp[(dk) + RK][(y + (dj)) * RP + v + (di) + DRS_SH_((dk) + RK, y + (dj))])
 #else
 #define DRS_OPERAND_(dk, dj, di)                                                               \
     (((di) == 0 && (y + (dj)) >= 0 && (y + (dj)) < RY)                                         \
          ? q[slot<PH>(dk)][clampi(y + (dj), 0, RY - 1)][v]                                     \
-         : sp[(dk) + RK][(y + (dj)) * RP + v + (di)])
+         : sp[(dk) + RK][(y + (dj)) * RP + v + (di) + DRS_SH_((dk) + RK, y + (dj))])
 #endif
 #define DRS_MUL_(dk, dj, di, c) acc = rmul(DRS_OPERAND_(dk, dj, di), (real)(c));
 #define DRS_FMA_(dk, dj, di, c) acc = rfma(DRS_OPERAND_(dk, dj, di), (real)(c), acc);
@@ -158,9 +179,10 @@ __device__ __forceinline__ bool iteration(real (&q)[K2][RY][kVec], const Stream&
             }
         }
     }
+#undef DRS_SH_
     // the oldest plane of the window is no longer needed: refill its stage
     __syncwarp();
-#if DRS_FLAT
+#if DRS_FLAT == 2
     if (n + LA < st.NIT) st.issue(n + LA);
 #else
     if (st.lane == 0 && n + LA < st.NIT) {
@@ -206,7 +228,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     st.N = p.N;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT ? 32 : 1);
+        for (int s = 0; s < ST; ++s) mbar_init(&st.bars[s], DRS_FLAT == 2 ? 32 : 1);
         fence_mbar_init();
         fence_proxy_async();
     }
@@ -258,7 +280,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         }
     }
 
-    if (DRS_FLAT || lane == 0) {
+    if (DRS_FLAT == 2 || lane == 0) {
         for (int n = 0; n < LA && n < st.NIT; ++n) st.issue(n);
     }
 

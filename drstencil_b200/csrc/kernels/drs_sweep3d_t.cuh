@@ -32,6 +32,10 @@
 #pragma once
 #include "drs_common.cuh"
 
+#if DRS_FLAT == 1
+#error "the fused 3D temporal kernel has no per-row TMA form: the generator selects DRS_FLAT 2 for it"
+#endif
+
 // How much of a source plane a thread takes from registers / its neighbour lanes instead of shared
 // memory (the kernel is shared-memory-bandwidth bound; B200, c4 depth 2: 589 / 646 / 657 / 667 / 687
 // GStencil/s for 0..4).  Kept as a switch for ablation (DRS_EXTRA_DEFINES="DRS_T3_OWNREG=n").

@@ -174,14 +174,19 @@ def test_knob_variants_keep_parity(built, name, kn):
     ("3d7pt_star", (24, 40, 129), dict(dtype="f32")), ("3d7pt_star", (24, 41, 130), dict(dtype="f32", rows_3d=6)),
     ("3d7pt_star", (24, 40, 131), dict(share_x=2, share_y=2)),      # shared ring has no flat form: private rings
 ])
-def test_unaligned_row_pitch_stays_on_the_tma_kernels_bit_exact(built, name, shape, kn):
-    """Rows that are not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32) have no tensor map; the sweep
-    kernels then fill the same ring of stages with element-sized cp.async (DRS_FLAT) instead of falling back to the
-    naive kernel -- the reference's emitted kernels handle any N at full speed through their i_ok guards
-    (codegen_2d.hpp:192-207).  Same chain, same bits; the frozen ring stays untouched."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_unaligned_row_pitch_stays_on_the_tma_kernels_bit_exact(built, name, shape, kn, mode, monkeypatch):
+    """Rows that are not a multiple of 16 bytes (odd N in fp64, N % 4 != 0 in fp32) cannot be described to TMA by rows,
+    and a TMA box must start on a 16-byte boundary.  The sweep kernels then fetch a tile as one TMA request per row
+    from the 16-byte boundary below the row's start, the consumers adding the row's shift (DRS_FLAT 1), or -- arrays
+    beyond 2^31 elements, forced here with DRS_FLAT_MODE=2 -- fill the same ring with element-sized cp.async
+    (DRS_FLAT 2), instead of falling back to the naive kernel: the reference's emitted kernels handle any N at full
+    speed through their i_ok guards (codegen_2d.hpp:192-207).  Same chain, same bits; the frozen ring stays untouched."""
     from oracle import oracle
+    if mode == 2:
+        monkeypatch.setenv("DRS_FLAT_MODE", "2")
     plan = _plan(name, shape, **kn)
-    assert plan.info.kernel_name.startswith("dr_") and "#define DRS_FLAT 1" in plan.source
+    assert plan.info.kernel_name.startswith("dr_") and "#define DRS_FLAT %d" % mode in plan.source
     f32 = kn.get("dtype") == "f32"
     dt = np.float32 if f32 else np.float64
     a0 = oracle.rand_array(shape, dt)
@@ -201,10 +206,14 @@ def test_unaligned_row_pitch_stays_on_the_tma_kernels_bit_exact(built, name, sha
     ("3d7pt_star", (40, 48, 131), dict(step=2)), ("3d9pt_cross", (36, 40, 67), dict(step=2)), ("3d7pt_star", (48, 50, 129), dict(step=3)),
     ("3d7pt_star", (40, 44, 131), dict(step=5)),                     # per-sub-step launches through scratch buffers
 ])
-def test_unaligned_row_pitch_temporal_kernels(built, name, shape, kn):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_unaligned_row_pitch_temporal_kernels(built, name, shape, kn, mode, monkeypatch):
     from oracle import oracle
+    if mode == 2:
+        monkeypatch.setenv("DRS_FLAT_MODE", "2")
     plan = _plan(name, shape, **kn)
-    assert plan.info.kernel_name.startswith("dr_") and "#define DRS_FLAT 1" in plan.source
+    fused3d = "drs_sweep3d_t.cuh" in plan.source       # the fused 3D temporal kernel only has the cp.async form
+    assert plan.info.kernel_name.startswith("dr_") and "#define DRS_FLAT %d" % (2 if fused3d else mode) in plan.source
     step = kn["step"]
     f32 = kn.get("dtype") == "f32"
     a64 = oracle.rand_array(shape)
@@ -219,15 +228,14 @@ def test_unaligned_row_pitch_temporal_kernels(built, name, shape, kn):
     assert np.array_equal(A.cpu().numpy()[ring], a0[ring])
 
 
-@pytest.mark.parametrize("name,odd,even,kn", [
-    ("2d5pt_star", (8191, 8191), (8192, 8192), dict()),
-    ("3d7pt_star", (767, 767, 767), (768, 768, 768), dict()),
-    ("2d9pt_box", (8191, 8191), (8192, 8192), dict(step=4)),
+@pytest.mark.parametrize("name,odd,even,kn,bar", [
+    ("2d5pt_star", (8191, 8191), (8192, 8192), dict(), 1.10),          # measured 0.97 - 1.07
+    ("3d7pt_star", (767, 767, 767), (768, 768, 768), dict(), 1.22),    # measured 1.14
+    ("2d9pt_box", (8191, 8191), (8192, 8192), dict(step=4), 1.30),     # measured 1.21
 ])
-def test_unaligned_row_pitch_is_no_performance_cliff(built, name, odd, even, kn):
-    """an odd N must not fall off a cliff (round 1: the naive kernel, ~10x slower).  The cp.async
-    ring costs instructions the TMA ring does not: measured on B200 (profiles/r02_unaligned_pitch.md) 1.3x (2D single
-    step), 1.4x (2D depth 4), 1.6x (3D) the time per point of the aligned size next to it -- the bar here is 2x."""
+def test_unaligned_row_pitch_is_no_performance_cliff(built, name, odd, even, kn, bar):
+    """an odd N must stay close to the aligned size next to it (round 1: the naive kernel, ~10x
+    slower; the cp.async form: 1.3x - 1.6x; per-row TMA: 0.97x / 1.14x / 1.21x, profiles/r02_unaligned_pitch.md)."""
     import torch
     per_point = []
     for shape in (odd, even):
@@ -236,13 +244,18 @@ def test_unaligned_row_pitch_is_no_performance_cliff(built, name, odd, even, kn)
         B = torch.zeros_like(A)
         _sweeps(plan, A, B, 4)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _sweeps(plan, A, B, 20)
-        e1.record()
-        torch.cuda.synchronize()
-        per_point.append(e0.elapsed_time(e1) / float(np.prod(shape)))
+        best = None
+        for _ in range(3):
+            e0.record()
+            _sweeps(plan, A, B, 20)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        per_point.append(best / float(np.prod(shape)))
         del A, B
-    assert per_point[0] <= 2.0 * per_point[1], per_point
+    print("unaligned / aligned time per point: %.3f" % (per_point[0] / per_point[1]))
+    assert per_point[0] <= bar * per_point[1], per_point
 
 
 @pytest.mark.parametrize("name,step", [("2d9pt_box", 4), ("3d7pt_star", 2), ("2d25pt_box", 1)])
