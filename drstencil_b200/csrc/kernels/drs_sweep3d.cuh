@@ -299,7 +299,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     if constexpr (SLAB) {
         const int face = slab_face(p, slab_chunk_order(p, (int)(((drs_i64)blockIdx.x * NW + warp) / ((drs_i64)p.nxs * p.nys))));
         if (face) {
-            __threadfence_system();  // this lane's stores (own planes and pushed ghost planes) before the signal
             __syncwarp();
             if (lane == 0) slab_arrive(p, face & 1, face & 2);
         }

@@ -265,7 +265,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         const int nxc2 = (p.nxs + SX - 1) / SX, nyc2 = (p.nys + SY - 1) / SY;
         const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((drs_i64)nxc2 * nyc2))));
         if (face) {
-            __threadfence_system();
             __syncwarp();
             if (lane == 0) slab_arrive(p, face & 1, face & 2);
         }

@@ -383,7 +383,6 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     if constexpr (SLAB) {                        // the unit of the slab protocol is the CTA
         const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((drs_i64)p.nxs * p.nys))));
         if (face) {                              // CTA-uniform
-            __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) slab_arrive(p, face & 1, face & 2);
         }

@@ -71,7 +71,7 @@ def main():
             a[1] += t
         total = sum(a[1] for a in agg.values())
         with open(os.path.join(out_dir, "%s_bench_launches.md" % tag), "w") as f:
-            f.write("# ncu launch list of `python bench.py --no-extras --steps 1 --warmup 3` (first %d launches)\n\n" % len(rows))
+            f.write("# ncu launch list of `python bench.py --no-extras --no-parity --steps 1 --warmup 3` (first %d launches)\n\n" % len(rows))
             f.write("cold-cache, serialised times: compare SHARES, not absolutes\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
             for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write("| `%s` | %d | %.3f | %.1f%% |\n" % (k, n, t * 1e3, 100 * t / total))
