@@ -59,6 +59,11 @@ CASES = [
     ("3d7pt_star", (40, 10, 12), dict(), 8, 5),
     ("3d7pt_star", (33, 10, 12), dict(step=2, fuse="algebraic"), 8, 4),
     ("3d9pt_cross", (26, 10, 12), dict(), 4, 3),
+    # a remainder thinner than 2*Halo joins its predecessor (round 1: slow = S + 1 with S = 2*Halo left a block of one
+    # row, below the thickness the schedule's correctness argument needs)
+    ("2d9pt_star", (9, 20), dict(), 6, 4),              # Halo 2, S = 2*Halo = 4, slow = 2*S + 1
+    ("2d5pt_star", (5, 24), dict(), 6, 2),              # Halo 1, S = 2, slow = 2*S + 1
+    ("3d7pt_star", (7, 10, 12), dict(step=2, fuse="algebraic"), 8, 4),   # Halo 2, S = 4, slow = S + 3
 ]
 
 

@@ -229,9 +229,9 @@ def test_unaligned_row_pitch_temporal_kernels(built, name, shape, kn, mode, monk
 
 
 @pytest.mark.parametrize("name,odd,even,kn,bar", [
-    ("2d5pt_star", (8191, 8191), (8192, 8192), dict(), 1.10),          # measured 0.97 - 1.07
-    ("3d7pt_star", (767, 767, 767), (768, 768, 768), dict(), 1.22),    # measured 1.14
-    ("2d9pt_box", (8191, 8191), (8192, 8192), dict(step=4), 1.30),     # measured 1.21
+    ("2d5pt_star", (8191, 8191), (8192, 8192), dict(), 1.15),          # measured 0.97 - 1.07
+    ("3d7pt_star", (767, 767, 767), (768, 768, 768), dict(), 1.30),    # measured 1.14 - 1.18
+    ("2d9pt_box", (8191, 8191), (8192, 8192), dict(step=4), 1.40),     # measured 1.21 - 1.27
 ])
 def test_unaligned_row_pitch_is_no_performance_cliff(built, name, odd, even, kn, bar):
     """an odd N must stay close to the aligned size next to it (round 1: the naive kernel, ~10x
