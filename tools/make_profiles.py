@@ -57,6 +57,27 @@ def main():
             summary[os.path.splitext(os.path.basename(f))[0]] = {k: v for k, v in s.items() if not isinstance(v, dict)}
             traffic[os.path.splitext(os.path.basename(f))[0].split("_", 1)[1]] = s.get("dram_bytes")
     json.dump(summary, open(os.path.join(out_dir, "%s_ncu_summary.json" % tag), "w"), indent=1, sort_keys=True)
+    # the same as a table
+    with open(os.path.join(out_dir, "%s_ncu_summary.md" % tag), "w") as f:
+        f.write("# %s -- Nsight Compute summary of the sweep kernels (B200, `ncu --set full --clock-control none --import-source on "
+                "-k regex:dr_ -s 3 -c 2` on `python -m drstencil_b200.tuner.run_one ...`, each only after the same command had "
+                "exited 0 without ncu; mean of the profiled launches)\n\n" % tag)
+        f.write("`prof_<preset>`: the preset's kernel on its own grid; `prof_c5slab`: the c5 preset on a 256 x 1536 x 1536 slab (54 GiB of "
+                "state is too much for full-set replays); `dram_c5`: DRAM bytes and duration of the c5 launches inside the bench command.\n\n")
+        f.write("| report | kernel | time | DRAM read | DRAM written | DRAM GB/s | DRAM % of peak | L2 bytes | L2 % | shared wavefronts | bank conflicts | "
+                "FP64 pipe | FMA pipe | issue active | warps active | regs | occupancy limit regs / smem (CTAs) |\n|" + "---|" * 17 + "\n")
+        g = lambda d, k, scale=1.0, fmt="%.1f": (fmt % (d[k] * scale)) if k in d else "-"
+        for name, d in sorted(summary.items()):
+            f.write("| `%s` | `%s` | %s ms | %s GB | %s GB | %s | %s %% | %s GB | %s %% | %s | %s | %s %% | %s %% | %s %% | %s %% | %s | %s / %s |\n" % (
+                name, d.get("kernel", "")[:40], g(d, "gpu__time_duration.sum", 1e3, "%.4f"), g(d, "dram__bytes_read.sum", 1e-9, "%.3f"),
+                g(d, "dram__bytes_write.sum", 1e-9, "%.3f"), g(d, "dram_gbs", 1.0, "%.0f"),
+                g(d, "dram__throughput.avg.pct_of_peak_sustained_elapsed"), g(d, "lts__t_bytes.sum", 1e-9, "%.2f"),
+                g(d, "lts__throughput.avg.pct_of_peak_sustained_elapsed"), g(d, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 1.0, "%.3g"),
+                g(d, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 1.0, "%.3g"),
+                g(d, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"), g(d, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                g(d, "smsp__issue_active.avg.pct_of_peak_sustained_active"), g(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                g(d, "launch__registers_per_thread", 1.0, "%.0f"), g(d, "launch__occupancy_limit_registers", 1.0, "%.0f"),
+                g(d, "launch__occupancy_limit_shared_mem", 1.0, "%.0f")))
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
     # launch list of the bench command: per-kernel totals and shares
     ll = os.path.join(ROOT, "gpurun_out", "launches.csv")
