@@ -54,6 +54,10 @@ struct KernelSpec {
     std::vector<double> fw;                 // w[dj + rj]
     std::vector<Term> fres;                 // residual terms (coefficient = K - w*h where that is not zero)
     int fops = 0;                           // arithmetic operations per output in factored form
+    // deferred scale of the factorised form: every sub-step evaluates K / fscale (h is divided by one of its own
+    // entries, which turns that entry's multiply into nothing), the values of level s carry a factor fscale^-s and
+    // the store multiplies by fscale^ts once.  1.0 = not used.
+    double fscale = 1.0;
     // `--fuse reuse`: the reference's forward/backward evaluation (drs_reuse.cuh); block shape rbx x rby
     bool reuse = false;
     int dist = 0, rbx = 128, rby = 1;
@@ -226,6 +230,16 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         s.e = std::max(s.e, std::abs(t.di));
     }
     if (s.ts > 1 && !(k.reserved[6] & 1)) factorise_rows(s);
+    if (s.ts > 1 && !s.factored && !std::getenv("DRS_NO_DEFERRED_SCALE")) {
+        // Deferred scale for the plain scatter forms (2D temporal, fused 3D temporal): every sub-step evaluates
+        // K / eta with eta = the coefficient of the first term an output receives, so that its partial sum starts
+        // as a copy instead of a product (3d7pt_star: 7 -> 6 operations per point and level); the store multiplies
+        // by eta^ts.  Tolerance-checked modes only (the bit-exact chain is never scaled).
+        for (const Term& t : s.chain) {
+            const int lead = s.dim == 3 ? t.dk : t.dj;
+            if (lead == -(s.dim == 3 ? s.rk : s.rj)) { if (t.coef != 0.0 && t.coef != 1.0) s.fscale = t.coef; break; }
+        }
+    }
     // --- geometry ---
     const long long slow = s.dim == 3 ? st.L : st.M;
     const long long slow_out = std::max<long long>(1, slow - 2 * s.halo);
@@ -381,6 +395,35 @@ inline bool factorise_rows(KernelSpec& s) {
     if (!found || best_ops * 5 > (int)s.chain.size() * 4) return false;   // want >= 20 % fewer operations
     s.factored = true;
     s.fops = best_ops;
+    // Deferred scale: dividing h by one of its entries gives the row pass a unit coefficient (one multiply less per
+    // point and level: 2d9pt_box 6 -> 5 operations); the residual terms are divided too, the row weights w are not
+    // affected (K / eta = w (x) (h / eta) + res / eta), and the store multiplies by eta^ts.  Chosen only when it
+    // removes an operation from the row pass.
+    auto hrow_ops = [&](const std::vector<double>& h) {
+        int terms = 0, adds = 0; bool unit = false;
+        if (h[E] != 0.0) { ++terms; unit = unit || h[E] == 1.0; }
+        for (int d = 1; d <= E; ++d) {
+            const double a = h[E - d], b = h[E + d];
+            if (a != 0.0 && a == b) { ++terms; ++adds; unit = unit || a == 1.0; }
+            else { if (a != 0.0) { ++terms; unit = unit || a == 1.0; } if (b != 0.0) { ++terms; unit = unit || b == 1.0; } }
+        }
+        return adds + (terms - 1) + (unit ? 0 : 1);
+    };
+    const int base = hrow_ops(s.fh);
+    double best_eta = 1.0; int best = base;
+    for (double eta : s.fh) {
+        if (eta == 0.0 || eta == 1.0) continue;
+        std::vector<double> h2 = s.fh;
+        for (double& v : h2) v /= eta;
+        const int ops = hrow_ops(h2);
+        if (ops < best) { best = ops; best_eta = eta; }
+    }
+    if (best_eta != 1.0 && s.ts >= 2 && !std::getenv("DRS_NO_DEFERRED_SCALE")) {   // (the switch is a development aid: A/B timing)
+        for (double& v : s.fh) v /= best_eta;
+        for (Term& t : s.fres) t.coef /= best_eta;
+        s.fscale = best_eta;
+        s.fops -= base - best;
+    }
     return true;
 }
 
@@ -401,20 +444,28 @@ inline void emit_scatter(std::ostringstream& o, const KernelSpec& s) {
     const int E = s.e, RJ = s.rj;
     if (s.factored) {
         o << "#define DRS_FACTORED 1\n#define DRS_HROW(U)";
-        bool first = true;
-        auto hterm = [&](const std::string& operand, double c) {
-            if (first) o << " \\\n    hacc = rmul(" << operand << ", (real)(" << lit17(c) << "));";
-            else o << " \\\n    hacc = rfma(" << operand << ", (real)(" << lit17(c) << "), hacc);";
-            first = false;
-        };
-        if (s.fh[E] != 0.0) hterm("U(0)", s.fh[E]);
+        // terms of h . u: the centre, then the symmetric pairs (one add, one coefficient) or single entries; a term
+        // with coefficient 1 goes first and costs nothing beyond its operand
+        std::vector<std::pair<std::string, double>> hterms;
+        if (s.fh[E] != 0.0) hterms.push_back({"U(0)", s.fh[E]});
         for (int d = 1; d <= E; ++d) {
             const double a = s.fh[E - d], b = s.fh[E + d];
-            if (a != 0.0 && a == b) hterm("radd(U(" + std::to_string(-d) + "), U(" + std::to_string(d) + "))", a);
+            if (a != 0.0 && a == b) hterms.push_back({"radd(U(" + std::to_string(-d) + "), U(" + std::to_string(d) + "))", a});
             else {
-                if (a != 0.0) hterm("U(" + std::to_string(-d) + ")", a);
-                if (b != 0.0) hterm("U(" + std::to_string(d) + ")", b);
+                if (a != 0.0) hterms.push_back({"U(" + std::to_string(-d) + ")", a});
+                if (b != 0.0) hterms.push_back({"U(" + std::to_string(d) + ")", b});
             }
+        }
+        for (size_t q = 0; q < hterms.size(); ++q)
+            if (hterms[q].second == 1.0) { std::swap(hterms[0], hterms[q]); break; }
+        for (size_t q = 0; q < hterms.size(); ++q) {
+            const std::string& operand = hterms[q].first;
+            const double c = hterms[q].second;
+            if (q == 0) {
+                if (c == 1.0) o << " \\\n    hacc = " << operand << ";";
+                else o << " \\\n    hacc = rmul(" << operand << ", (real)(" << lit17(c) << "));";
+            } else if (c == 1.0) o << " \\\n    hacc = radd(hacc, " << operand << ");";
+            else o << " \\\n    hacc = rfma(" << operand << ", (real)(" << lit17(c) << "), hacc);";
         }
         o << "\n";
     }
@@ -435,8 +486,8 @@ inline void emit_scatter(std::ostringstream& o, const KernelSpec& s) {
             for (const Term& t : s.fres)
                 if (t.dj == dj) add_term("U(" + std::to_string(t.di) + ")", t.coef);
         } else {
-            for (const Term& t : s.chain)
-                if (t.dj == dj) add_term("U(" + std::to_string(t.di) + ")", t.coef);
+            for (const Term& t : s.chain)      // (un-factorised: the chain's coefficients divided by the deferred scale)
+                if (t.dj == dj) add_term("U(" + std::to_string(t.di) + ")", t.coef / s.fscale);
         }
         if (!started) o << " \\\n    " << P << " = (real)0;";
     }
@@ -453,8 +504,12 @@ inline void emit_scatter3(std::ostringstream& o, const KernelSpec& s) {
         for (const Term& t : s.chain) {
             if (t.dk != dk) continue;
             const std::string U = "U(" + std::to_string(t.dj) + ", " + std::to_string(t.di) + ")";
-            if (!started) o << " \\\n    " << P << " = rmul(" << U << ", (real)(" << lit17(t.coef) << "));";
-            else o << " \\\n    " << P << " = rfma(" << U << ", (real)(" << lit17(t.coef) << "), " << P << ");";
+            const double c = t.coef / s.fscale;         // deferred scale: a coefficient of 1 costs no multiply
+            if (!started) {
+                if (c == 1.0) o << " \\\n    " << P << " = " << U << ";";
+                else o << " \\\n    " << P << " = rmul(" << U << ", (real)(" << lit17(c) << "));";
+            } else if (c == 1.0) o << " \\\n    " << P << " = radd(" << P << ", " << U << ");";
+            else o << " \\\n    " << P << " = rfma(" << U << ", (real)(" << lit17(c) << "), " << P << ");";
             started = true;
         }
         if (!started) o << " \\\n    " << P << " = (real)0;";
@@ -526,6 +581,7 @@ inline std::string generate_tu(const KernelSpec& s) {
     emit_chain(o, "DRS_CHAIN", s.chain);
     if (s.ts > 1 && s.dim == 2) emit_scatter(o, s);
     if (s.fused3d) emit_scatter3(o, s);
+    if (s.ts > 1 && s.fscale != 1.0) o << "#define DRS_OUT_SCALE (" << lit17(std::pow(s.fscale, s.ts)) << ")\n";
     emit_chain(o, "DRS_GOLD_CHAIN", s.gold);
     if (s.reuse) o << "#include \"drs_reuse.cuh\"\n";
     else if (s.tma_ok)

@@ -178,7 +178,14 @@ __device__ __forceinline__ void row_step(real (&w)[NLV][R2][SW], const real* __r
             if (s == TS && n >= t.n_first && n < t.n_end) {
                 real o[C];
 #pragma unroll
-                for (int v = 0; v < C; ++v) o[v] = w[TS - 1][mod_r2(PH - RJ)][v];
+                for (int v = 0; v < C; ++v) {
+#ifdef DRS_OUT_SCALE
+                    // the factorised sub-steps evaluated K / eta: level TS carries eta^-TS (generate.hpp: fscale)
+                    o[v] = rmul(w[TS - 1][mod_r2(PH - RJ)][v], (real)DRS_OUT_SCALE);
+#else
+                    o[v] = w[TS - 1][mod_r2(PH - RJ)][v];
+#endif
+                }
                 store_row(t, n, o);
             }
         }

@@ -230,7 +230,14 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
                 if (y >= c.y_lo && y < c.y_hi) {
                     real o[kVec];
 #pragma unroll
-                    for (int v = 0; v < kVec; ++v) o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
+                    for (int v = 0; v < kVec; ++v) {
+#ifdef DRS_OUT_SCALE
+                        // the sub-steps evaluated K / eta: level TS carries eta^-TS (generate.hpp: fscale)
+                        o[v] = rmul(pw[TS - 1][mod_k2(PH - RK)][y][v], (real)DRS_OUT_SCALE);
+#else
+                        o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
+#endif
+                    }
                     const drs_i64 off = (drs_i64)y * c.N;
                     if (c.v_lo <= 0 && c.v_hi >= kVec) {
                         stg_vec(orow + off, o);
