@@ -21,7 +21,7 @@ def _p(*parts):
 # workload -> (stc file, dimensionality, configuration name == winners[0].name of profiles/r02_tune_<workload>.json)
 TUNED = {
     "c1": (_p("baseline", "c1_2d5pt_star.stc"), 2, "fu1d0bx32sn128u4bmx2mf5st2"),
-    "c2": (_p("baseline", "c2_2d9pt_box.stc"), 2, "fu4d0bx128sn256u4bmx2mf5st2"),
+    "c2": (_p("baseline", "c2_2d9pt_box.stc"), 2, "fu4d0bx64sn256u4bmx2mf5st2mb4"),
     "c3": (_p("baseline", "c3_2d25pt_box.stc"), 2, "fu1d0bx64sn32u8bmx1mf5st2f32"),
     # c4 / c5: four warps (2 x 2) share one input ring per CTA (drs_sweep3d_cta.cuh); c5 with eight rows per thread
     # (9.32 ms sustained vs 9.50 for round 1's private rings with six rows)
