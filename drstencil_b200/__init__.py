@@ -175,7 +175,7 @@ class Knobs:
     """The generator's options (main.cpp:12-56), same names, same defaults.  Only options passed
     explicitly constrain the engine; the rest are chosen for B200.  Engine-only tuning overrides:
     stages, min_blocks, warps, rows_3d (RY), rows_per_stage, vectors (128-bit vectors per thread, 2D),
-    share_x / share_y (experimental: warps of a CTA that share one input ring in the single-step 3D sweep)."""
+    share_x / share_y (warps of a CTA that share one input ring in the single-step 3D sweep: the c4 / c5 presets)."""
 
     def __init__(self, **kw):
         self.values = dict(_KNOB_DEFAULTS)
@@ -222,7 +222,7 @@ class Knobs:
         k.reserved[4] = self.extra["rows_per_stage"]
         k.reserved[5] = self.extra["vectors"]
         k.reserved[6] = (1 if self.extra["no_factor"] else 0) | (2 if self.extra["no_fused3d"] else 0)
-        if self.extra["share_x"] > 1 or self.extra["share_y"] > 1:      # experimental CTA-shared 3D ring
+        if self.extra["share_x"] > 1 or self.extra["share_y"] > 1:      # CTA-shared 3D ring (drs_sweep3d_cta.cuh)
             k.reserved[6] |= ((max(1, self.extra["share_x"]) - 1) & 3) << 2 | ((max(1, self.extra["share_y"]) - 1) & 3) << 4
         return k
 

@@ -1235,13 +1235,13 @@ int drs_run_slab(drs_plan* p, int iterations, void* stream_, int* sweeps) {
     return DRS_OK;
 }
 
-// EXPERIMENTAL executor of drs_plan_slab_schedule (written against the CPU-verified planner; not yet run on
-// GPUs -- nothing in the package or the bench calls it).  One rank's share of a slab-decomposed host-buffer
-// run: h_own holds the rank's own planes; uploads, sweeps and downloads run on three streams chained by
-// events as in run_host_streamed; launches that touch a face are bracketed by the slab flag kernels, and the
-// upload that brings a face's level-0 planes is followed by a peer copy of them into the neighbour's ghosts.
-// Flags are monotone: this call uses the values flag_base + 1 ... flag_base + sweeps + 1; the caller separates
-// calls by a barrier and advances flag_base by at least sweeps + 2.
+// Executor of drs_plan_slab_schedule (validated on 2, 4 and 8 GPUs: bit-exact against the single-GPU run,
+// tools/slab_check.py and bench.py's in-run parity).  One rank's share of a slab-decomposed host-buffer run: h_own
+// holds the rank's own planes; uploads, sweeps and downloads run on three streams chained by events as in
+// run_host_streamed; launches that touch a face are bracketed by the slab flag kernels, and the upload that brings a
+// face's level-0 planes is followed by a peer copy of them into the neighbour's ghosts.  Flags are monotone: this call
+// uses the values slab_seq + 1 ... slab_seq + sweeps + 1 and leaves slab_seq at the largest one; the caller separates
+// calls by a barrier.
 int drs_run_host_slab(drs_plan* p, void* h_own, int iterations, int up_skew, float* device_ms) {
     if (!p || !h_own) return fail(DRS_E_ARG, "null argument");
     if (!p->slab || !p->my_bases[0] || !p->my_bases[1]) return fail(DRS_E_ARG, "call drs_plan_set_slab and drs_plan_set_peers first");

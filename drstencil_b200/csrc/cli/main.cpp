@@ -62,7 +62,7 @@ Extensions:
 --info                  Print the chosen tile geometry and the reference macros (Halo Dist Range).
 --allow-no-reuse        Do not stop where the reference prints "No data to reuse".
 --stages --warps --min-blocks --vectors --rows-3d --rows-per-stage <num>   tile overrides.
---share-x --share-y <1..4>   experimental: warps of a CTA that share one input ring (3D, single step).
+--share-x --share-y <1..4>   warps of a CTA along x / y that share one input ring (3D, single step).
         )";
 
 static int illegal_exit() {
@@ -105,7 +105,7 @@ int main(int argc, char** argv) {
         if (a == "--run") { run = true; continue; }
         if (a == "--info") { info = true; continue; }
         if (a == "--allow-no-reuse") { allow_no_reuse = true; continue; }
-        if (a == "--share-x" || a == "--share-y") {      // experimental: CTA-shared ring (drstencil.h, reserved[6])
+        if (a == "--share-x" || a == "--share-y") {      // CTA-shared ring (drstencil.h, reserved[6])
             if (i == argc - 2) illegal_exit();
             const int v = atoi(argv[++i]);
             if (v < 1 || v > 4) illegal_exit();

@@ -43,7 +43,7 @@ struct KernelSpec {
     int base_order = 0;         // Halo of one sub-step
     // 3D `--step n` fused in one kernel (drs_sweep3d_t.cuh): a CTA of nw warps stacked along y
     bool fused3d = false;
-    // experimental (engine override share_x / share_y): single-step 3D sweep whose sx * sy warps share one
+    // engine override share_x / share_y (the c4 / c5 presets): single-step 3D sweep whose sx * sy warps share one
     // input ring per CTA (drs_sweep3d_cta.cuh) instead of one private ring per warp
     bool share3d = false;
     int sx = 1, sy = 1;

@@ -220,40 +220,36 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         } else if (n >= c.n_first && n < c.n_end) {
             const drs_i64 z = c.z_out0 + n;
             const drs_i64 row0 = c.y_first * c.N + c.x_first;
-            real* orow = c.out + z * c.M * c.N + row0;
-            const bool push_lo = c.peer_lo != nullptr && z >= c.lo0 && z < c.lo1;
-            const bool push_hi = c.peer_hi != nullptr && z >= c.hi0 && z < c.hi1;
-            real* plo = push_lo ? c.peer_lo + (z + c.lo_shift) * c.M * c.N + row0 : nullptr;
-            real* phi = push_hi ? c.peer_hi + (z + c.hi_shift) * c.M * c.N + row0 : nullptr;
+            // one pass per destination (own array, then the neighbours' ghost planes on the boundary planes of a slab):
+            // a single base pointer is live at a time -- with all three live the slab entry point spilled in this loop
+            auto store_plane = [&](real* base) {
 #pragma unroll
-            for (int y = 0; y < RY; ++y) {
-                if (y >= c.y_lo && y < c.y_hi) {
-                    real o[kVec];
+                for (int y = 0; y < RY; ++y) {
+                    if (y >= c.y_lo && y < c.y_hi) {
+                        real o[kVec];
 #pragma unroll
-                    for (int v = 0; v < kVec; ++v) {
+                        for (int v = 0; v < kVec; ++v) {
 #ifdef DRS_OUT_SCALE
-                        // the sub-steps evaluated K / eta: level TS carries eta^-TS (generate.hpp: fscale)
-                        o[v] = rmul(pw[TS - 1][mod_k2(PH - RK)][y][v], (real)DRS_OUT_SCALE);
+                            // the sub-steps evaluated K / eta: level TS carries eta^-TS (generate.hpp: fscale)
+                            o[v] = rmul(pw[TS - 1][mod_k2(PH - RK)][y][v], (real)DRS_OUT_SCALE);
 #else
-                        o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
+                            o[v] = pw[TS - 1][mod_k2(PH - RK)][y][v];
 #endif
-                    }
-                    const drs_i64 off = (drs_i64)y * c.N;
-                    if (c.v_lo <= 0 && c.v_hi >= kVec) {
-                        stg_vec(orow + off, o);
-                        if (push_lo) stg_vec(plo + off, o);
-                        if (push_hi) stg_vec(phi + off, o);
-                    } else {
+                        }
+                        real* dst = base + (drs_i64)y * c.N;
+                        if (c.v_lo <= 0 && c.v_hi >= kVec) {
+                            stg_vec(dst, o);
+                        } else {
 #pragma unroll
-                        for (int v = 0; v < kVec; ++v)
-                            if (v >= c.v_lo && v < c.v_hi) {
-                                orow[off + v] = o[v];
-                                if (push_lo) plo[off + v] = o[v];
-                                if (push_hi) phi[off + v] = o[v];
-                            }
+                            for (int v = 0; v < kVec; ++v)
+                                if (v >= c.v_lo && v < c.v_hi) dst[v] = o[v];
+                        }
                     }
                 }
-            }
+            };
+            store_plane(c.out + z * c.M * c.N + row0);
+            if (c.peer_lo != nullptr && z >= c.lo0 && z < c.lo1) store_plane(c.peer_lo + (z + c.lo_shift) * c.M * c.N + row0);
+            if (c.peer_hi != nullptr && z >= c.hi0 && z < c.hi1) store_plane(c.peer_hi + (z + c.hi_shift) * c.M * c.N + row0);
         }
     }
     // published planes visible to every warp; the input stage is consumed by all of them
@@ -293,8 +289,9 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.tmap = &tmap;
     c.fault = p.fault;
 
-    const drs_i64 tile = blockIdx.x;
-    const drs_i64 per_chunk = (drs_i64)p.nxs * p.nys;
+    // one tile per CTA and at most 2^31 - 1 CTAs per launch (capi.cpp): 32-bit index arithmetic
+    const unsigned int tile = blockIdx.x;
+    const unsigned int per_chunk = (unsigned int)p.nxs * (unsigned int)p.nys;
     const int zc = SLAB ? slab_chunk_order(p, (int)(tile / per_chunk)) : (int)(tile / per_chunk);
     const int rem = (int)(tile % per_chunk);
     const int cy = rem / p.nxs, cx = rem % p.nxs;
@@ -388,7 +385,7 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
         if (!phases<0>(pw, c, n0)) return;       // watchdog: every warp of the CTA fails the same wait
     }
     if constexpr (SLAB) {                        // the unit of the slab protocol is the CTA
-        const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((drs_i64)p.nxs * p.nys))));
+        const int face = slab_face(p, slab_chunk_order(p, (int)(blockIdx.x / ((unsigned int)p.nxs * (unsigned int)p.nys))));
         if (face) {                              // CTA-uniform
             __syncthreads();
             if (threadIdx.x == 0) slab_arrive(p, face & 1, face & 2);

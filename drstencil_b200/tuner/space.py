@@ -36,7 +36,7 @@ class Config:
     rows_3d: int = 0
     dtype: str = "f64"
     fuse: str = "temporal"
-    # experimental: warps of a CTA along x / y that share one input ring (single-step 3D sweep)
+    # warps of a CTA along x / y that share one input ring (single-step 3D sweep)
     share_x: int = 1
     share_y: int = 1
     dim: int = 2        # selects the name grammar (the reference has one per dimensionality)

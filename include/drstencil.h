@@ -68,7 +68,7 @@ typedef struct drs_knobs {
      * [0] ring stages  [1] __launch_bounds__ minimum blocks per SM  [2] warps per CTA
      * [3] rows per thread in 3D  [4] rows per TMA stage in 2D  [5] 128-bit vectors per thread in 2D
      * [6] bit 0: no row factorisation, bit 1: 3D temporal depth as per-sub-step launches instead of the fused kernel,
- *     bits 2-3 / 4-5 (experimental): warps of a CTA along x / y, minus one, that share one input ring in the
+ *     bits 2-3 / 4-5: warps of a CTA along x / y, minus one, that share one input ring in the
  *     single-step 3D sweep (0 = one private ring per warp) */
     int reserved[7];
 } drs_knobs;
