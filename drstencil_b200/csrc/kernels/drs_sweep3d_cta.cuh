@@ -177,7 +177,14 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     const drs_i64 cta = blockIdx.x;
     const int zc = SLAB ? slab_chunk_order(p, (int)(cta / per_chunk)) : (int)(cta / per_chunk);
     const int rem = (int)(cta % per_chunk);
+#ifdef DRS_S3C_YFAST      // ablation (DRS_EXTRA_DEFINES): y-adjacent CTA tiles consecutive in launch order instead of x-adjacent
+    const int cys = rem % nyc, cxs = rem / nyc;
+#elif defined(DRS_S3C_BLOCKED)   // ablation: 2 x 2 groups of CTA tiles consecutive in launch order
+    const int g = rem >> 2, gx = g % ((nxc + 1) >> 1), gy = g / ((nxc + 1) >> 1);
+    const int cxs = 2 * gx + (rem & 1), cys = 2 * gy + ((rem >> 1) & 1);
+#else
     const int cys = rem / nxc, cxs = rem % nxc;
+#endif
 
     Stream st;
     st.ring = smem_raw;
