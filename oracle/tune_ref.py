@@ -52,30 +52,41 @@ HAND_PICKED = {
 MAX_THREADS_LG2, MAX_SHM_LG2 = 10, 15          # tuning.py:9-10
 
 
+def filter_2d(v, order):
+    """FilterParams, benchmarks/2d5pt_star/tuning.py:13-48."""
+    step, dist, bs, streaming, sn, unroll, bmx, mx, bmy, my, mf, prefetch = v
+    shm = (step * order + 1) * (mx * bs[0]) if streaming else (mx * bs[0]) * (my * bs[1])
+    if shm > 2 ** (MAX_SHM_LG2 - 3):
+        return False
+    if dist > step * order or dist < (step - 1) * order:
+        return False
+    if step * order * 2 >= bs[0] * mx:
+        return False
+    if streaming:
+        if bs[1] > 1 or my > 1:
+            return False
+    else:
+        if sn > 8 or unroll > 4:
+            return False
+        if bs[0] * bs[1] > 2 ** MAX_THREADS_LG2 or step * order * 2 >= bs[1] * my:
+            return False
+    if (bmx and mx == 1) or (bmy and my == 1):
+        return False
+    return True
+
+
 def space_2d(step, order):
-    """tuning.py:13-48 (FilterParams) over tuning.py:124-139 (the product), 2D."""
-    out = []
+    """tuning.py:13-48 (FilterParams) over tuning.py:124-139 (the product), 2D, with the workload's step and the
+    dist values the filter admits for it."""
     dists = [d for d in range(1, step * order + 1) if (step - 1) * order <= d <= step * order]
     blocks = [b for b in itertools.product([2 ** i for i in range(0, 10)], repeat=2) if b[0] * b[1] < 2 ** MAX_THREADS_LG2]
+    out = []
     for dist, bs, streaming, sn, unroll, bmx, mx, bmy, my, mf, prefetch in itertools.product(
             dists, blocks, [False, True], [8, 16, 32, 64], [4, 8], [False, True], [1, 2, 4], [False, True], [1, 2, 4],
             [5], [False, True]):
-        shm = (step * order + 1) * (mx * bs[0]) if streaming else (mx * bs[0]) * (my * bs[1])
-        if shm > 2 ** (MAX_SHM_LG2 - 3):
-            continue
-        if step * order * 2 >= bs[0] * mx:
-            continue
-        if streaming:
-            if bs[1] > 1 or my > 1:
-                continue
-        else:
-            if sn > 8 or unroll > 4:
-                continue
-            if bs[0] * bs[1] > 2 ** MAX_THREADS_LG2 or step * order * 2 >= bs[1] * my:
-                continue
-        if (bmx and mx == 1) or (bmy and my == 1):
-            continue
-        out.append((step, dist, bs, streaming, sn, unroll, bmx, mx, bmy, my, mf, prefetch))
+        v = (step, dist, bs, streaming, sn, unroll, bmx, mx, bmy, my, mf, prefetch)
+        if filter_2d(v, order):
+            out.append(v)
     return out
 
 
@@ -106,22 +117,32 @@ def name_2d(v):
     return s
 
 
+def filter_3d(v, order):
+    """FilterParams, benchmarks/3d7pt_star/tuning.py:13-36."""
+    step, dist, bs, sn, unroll, bmx, mx, bmy, my, mf, prefetch = v
+    if (step * order + 1) * (mx * bs[0]) * (my * bs[1]) > 2 ** (MAX_SHM_LG2 - 3):
+        return False
+    if dist > step * order or dist < (step - 1) * order:
+        return False
+    if step * order * 2 >= min(bs[0] * mx, bs[1] * my):
+        return False
+    if bs[0] <= 8:
+        return False
+    if (bmx and mx == 1) or (bmy and my == 1):
+        return False
+    return True
+
+
 def space_3d(step, order):
     """benchmarks/3d7pt_star/tuning.py:13-36 over :108-122."""
-    out = []
     dists = [d for d in range(1, step * order + 1) if (step - 1) * order <= d <= step * order]
     blocks = [b for b in itertools.product([2 ** i for i in range(3, 7)], repeat=2) if b[0] * b[1] <= 2 ** MAX_THREADS_LG2]
+    out = []
     for dist, bs, sn, unroll, bmx, mx, bmy, my, mf, prefetch in itertools.product(
             dists, blocks, [8, 16, 32, 64], [4, 8], [False, True], [1, 2, 4], [False, True], [1, 2, 4], [5], [False, True]):
-        if (step * order + 1) * (mx * bs[0]) * (my * bs[1]) > 2 ** (MAX_SHM_LG2 - 3):
-            continue
-        if step * order * 2 >= min(bs[0] * mx, bs[1] * my):
-            continue
-        if bs[0] <= 8:
-            continue
-        if (bmx and mx == 1) or (bmy and my == 1):
-            continue
-        out.append((step, dist, bs, sn, unroll, bmx, mx, bmy, my, mf, prefetch))
+        v = (step, dist, bs, sn, unroll, bmx, mx, bmy, my, mf, prefetch)
+        if filter_3d(v, order):
+            out.append(v)
     return out
 
 
