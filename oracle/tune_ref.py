@@ -31,8 +31,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-sys.path.insert(0, HERE)
-import build_ref  # noqa: E402
+if __package__:                         # imported as oracle.tune_ref (tests)
+    from . import build_ref
+else:                                   # run as a script: load the sibling by path, leaving sys.path alone
+    import importlib.util
+    _spec = importlib.util.spec_from_file_location("build_ref", os.path.join(HERE, "build_ref.py"))
+    build_ref = importlib.util.module_from_spec(_spec)
+    _spec.loader.exec_module(build_ref)
 
 TUNE = os.path.join(build_ref.OUT, "tune")
 BEST = os.path.join(HERE, "ref_best.json")

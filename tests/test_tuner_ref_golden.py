@@ -10,8 +10,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import tune_ref  # noqa: E402
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import tune_ref  # noqa: E402
 
 from drstencil_b200.tuner import space  # noqa: E402
 
