@@ -56,6 +56,7 @@ struct Driver {
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
     CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;   // optional
+    CUresult (*OccupancyMaxActiveBlocks)(int*, CUfunction, int, size_t) = nullptr;                 // optional (DRS_DEBUG_OCC)
 };
 
 Driver& driver() {
@@ -92,6 +93,10 @@ Driver& driver() {
             void* fp = nullptr;
             if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &fp, cudaEnableDefault, &q) == cudaSuccess && fp)
                 d.StreamWriteValue64 = (decltype(d.StreamWriteValue64))fp;
+            else cudaGetLastError();
+            fp = nullptr;
+            if (cudaGetDriverEntryPoint("cuOccupancyMaxActiveBlocksPerMultiprocessor", &fp, cudaEnableDefault, &q) == cudaSuccess && fp)
+                d.OccupancyMaxActiveBlocks = (decltype(d.OccupancyMaxActiveBlocks))fp;
             else cudaGetLastError();
         }
         d.ok = ok;
@@ -350,6 +355,19 @@ int ensure_loaded(drs_plan* p) {
         }
         d.FuncGetAttribute(&p->regs, CU_FUNC_ATTRIBUTE_NUM_REGS, p->f_sweep);
         d.FuncGetAttribute(&p->spill, CU_FUNC_ATTRIBUTE_LOCAL_SIZE_BYTES, p->f_sweep);
+        // development aid: DRS_CARVEOUT=<percent> states a shared-memory carve-out preference for the sweep kernels
+        // (default: the driver's own choice)
+        if (const char* co = std::getenv("DRS_CARVEOUT")) {
+            const int pct = std::atoi(co);
+            d.FuncSetAttribute(p->f_sweep, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct);
+            if (p->f_slab) d.FuncSetAttribute(p->f_slab, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, pct);
+        }
+        if (std::getenv("DRS_DEBUG_OCC") && d.OccupancyMaxActiveBlocks) {     // development aid: resident CTAs per SM
+            int nb = -1;
+            d.OccupancyMaxActiveBlocks(&nb, p->f_sweep, p->spec.nw * 32, (size_t)smem);
+            std::fprintf(stderr, "drs: dr_%s: %d CTAs of %d threads per SM (%d registers, %d bytes of shared memory)\n", nm.c_str(), nb,
+                         p->spec.nw * 32, p->regs, smem);
+        }
     }
     r = d.ModuleGetFunction(&p->f_gold, p->mod, ("gold_" + nm).c_str());
     if (r != CUDA_SUCCESS) return fail(DRS_E_CUDA, "cuModuleGetFunction(gold_): " + cu_err(r));

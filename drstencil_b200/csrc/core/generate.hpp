@@ -36,6 +36,9 @@ struct KernelSpec {
     // {total, 1} tensor map, consumers add the row's shift; 2 = the warp fills the stages itself with cp.async
     // (arrays of 2^31 elements or more, the fused 3D temporal kernel).  Scalar stores in both.
     int flat = 0;
+    // 3D arrays far beyond the L2: plane loads carry an L2 evict_last policy, so that the tile halos the neighbouring CTAs
+    // re-read outlive the output lines streaming through the cache (drs_common.cuh: DRS_LD_HINT)
+    bool keep_planes = false;
     // 3D `--step n` in temporal mode: n launches of the single-step kernel with frozen rings of
     // r, 2r, ... n*r through plan-owned scratch buffers (sub-steps exactly as a fused kernel would
     // evaluate them; not yet fused in one kernel -- no HBM saving, but no 25/35-point operator either)
@@ -171,6 +174,10 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         // development aid / tests: DRS_FLAT_MODE=2 forces the cp.async form on small grids too
         if (const char* e = std::getenv("DRS_FLAT_MODE")) if (std::atoi(e) == 2) s.flat = 2;
     }
+    // (measured on B200, c5: 388.5 -> 393.0 GStencil/s, depth 2 644.5 -> 649.6; evict_first instead: 321 / 463;
+    // DRS_NO_LD_HINT is the A/B switch)
+    s.keep_planes = s.dim == 3 && !s.flat && !std::getenv("DRS_NO_LD_HINT") &&
+                    (long double)st.L * (long double)st.M * (long double)st.N * (s.dtype == DRS_F64 ? 8 : 4) >= 1073741824.0L;
     bool temporal = (k.fuse == DRS_FUSE_TEMPORAL) && k.step > 1;
     if (temporal) {
         // The reference multiplies the operator out and prints the result with 6 significant digits
@@ -290,7 +297,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         if ((knob_given(k, KB_BMY) || knob_given(k, KB_CMY)) && my >= 1) s.ry = std::min(32, 4 * my);
     }
     // reserved[] carries engine-only tuning overrides (the tuner's extra axes); 0 = keep
-    if (k.reserved[0] > 0) s.st = pow2_ceil(k.reserved[0]);
+    if (k.reserved[0] > 0) s.st = s.fused3d ? std::max(2, k.reserved[0]) : pow2_ceil(k.reserved[0]);   // (the fused 3D temporal ring takes any depth)
     if (k.reserved[2] > 0) s.nw = k.reserved[2];
     if (k.reserved[3] > 0 && s.dim == 3) s.ry = k.reserved[3];
     if (k.reserved[4] > 0 && s.dim == 2) s.rb = pow2_floor(k.reserved[4]);
@@ -307,7 +314,7 @@ inline std::string choose_spec(const Stencil& base_in, const drs_knobs& k, Kerne
         // the reference happily emits a program) is thinned until it does -- rows per thread first, then warps
         if (s.st < 2) s.st = 2;
         while (s.smem_bytes() > 227 * 1024 && s.ry > 1) s.ry = std::max(1, s.ry / 2);
-        while (s.smem_bytes() > 227 * 1024 && s.st > 2) s.st /= 2;
+        while (s.smem_bytes() > 227 * 1024 && s.st > 2) s.st = std::max(2, s.st / 2);
         while (s.smem_bytes() > 227 * 1024 && s.nw > 2 && (s.nw / 2) * s.ry - 2 * (s.ts - 1) * s.rj >= 1) s.nw /= 2;
     }
     {
@@ -568,6 +575,7 @@ inline std::string generate_tu(const KernelSpec& s) {
             o << "#define " << item.substr(0, eq) << " " << (eq == std::string::npos ? "1" : item.substr(eq + 1)) << "\n";
         }
     }
+    if (s.keep_planes) o << "#ifndef DRS_LD_HINT\n#define DRS_LD_HINT 1\n#endif\n";
     if (s.reuse) {
         o << "#define DRS_DIST " << s.dist << "\n#define DRS_RBX " << s.rbx << "\n#define DRS_RBY " << s.rby << "\n";
         emit_chain(o, "DRS_FWD_SLOW", s.fwd_slow);

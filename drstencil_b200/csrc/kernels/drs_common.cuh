@@ -220,11 +220,29 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map, int
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
+// L2 policy experiments (DRS_EXTRA_DEFINES; 0 = none, the shipped setting -- DESIGN.md 3.5 has the measurements):
+//   DRS_LD_HINT  1 / 2: the 3D plane loads carry an L2 evict_last / evict_first policy
+//   DRS_ST_HINT  1: output vectors are stored with st.global.cs (streaming)
+#ifndef DRS_LD_HINT
+#define DRS_LD_HINT 0
+#endif
+#ifndef DRS_ST_HINT
+#define DRS_ST_HINT 0
+#endif
 __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map, int x, int y, int z, drs_u64* bar) {
+#if DRS_LD_HINT
+    // the fixed encodings of createpolicy.fractional.L2::evict_last / evict_first with fraction 1.0
+    const drs_u64 policy = DRS_LD_HINT == 1 ? 0x14F0000000000000ull : 0x12F0000000000000ull;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+#else
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
+#endif
 }
 // DRS_FLAT == 1: one row of a tile; x = flat element index of the box start (a multiple of kVec)
 __device__ __forceinline__ void tma_load_row(void* dst, const TensorMap* map, int x, drs_u64* bar) {
@@ -324,11 +342,16 @@ __device__ __forceinline__ void stg_vec(real* p, const real (&v)[kVec]) {
             return;
         }
     }
+#if DRS_ST_HINT
+    if constexpr (sizeof(real) == 8) __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+    else __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+#else
     if constexpr (sizeof(real) == 8) {
         *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     } else {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
+#endif
 }
 
 }  // namespace drs

@@ -55,6 +55,15 @@
 #endif
 #endif
 
+// Store path of the top level (ablation switch, DRS_EXTRA_DEFINES="DRS_T3_LEANSTORE=0|1").
+//   0  per row: range tests on y and on the vector's columns, 64-bit address from (z, row, column)
+//   1  one per-thread output pointer and one packed mask (storable rows, first / last storable column of the vector):
+//      the tile loses whole vectors per level, so away from the grid edge a thread stores whole vectors or nothing --
+//      predicated 128-bit stores at uniform row offsets, no branches
+#ifndef DRS_T3_LEANSTORE
+#define DRS_T3_LEANSTORE 0
+#endif
+
 namespace drs {
 namespace s3t {
 
@@ -71,7 +80,10 @@ constexpr int PLANE_BYTES = WB * YB * (int)sizeof(real);           // bytes the 
 constexpr int PLANE_STRIDE = (RP * YB * (int)sizeof(real) + 127) / 128 * 128;
 constexpr int NLV = TS - 1;                                     // intermediate levels kept in shared memory
 constexpr int DEPTH = 2 * TS * RK + TS - 1;
-static_assert((ST & (ST - 1)) == 0, "stage count is a power of two");
+static_assert(ST >= 2, "at least two stages");
+// ring slot and mbarrier phase of input plane n (any stage count; n is CTA-uniform, so this is uniform-datapath work)
+__device__ __forceinline__ int ring_slot(int n) { return (ST & (ST - 1)) == 0 ? (n & (ST - 1)) : n % ST; }
+__device__ __forceinline__ drs_u32 ring_phase(int n) { return (drs_u32)((n / ST) & 1); }
 static_assert(TS >= 2, "single-step sweeps use drs_sweep3d.cuh");
 static_assert(WU > 0 && TYU > 0, "tile too small for this depth");
 
@@ -93,6 +105,8 @@ struct Ctx {
     int y_lo, y_hi;          // storable tile rows of this warp: y_lo <= y < y_hi
     drs_i64 z_out0;
     int n_first, n_end;
+    real* optr;              // DRS_T3_LEANSTORE: where tile row 0 / element 0 of this thread lands for iteration 0
+    unsigned int smask;      // bits 0-7 storable rows, 8-15 first storable element of the vector, 16-23 one past the last
     drs_i64 M, N;
     real* out;
     // slab mode: boundary output planes are also stored into the neighbours' ghost planes (NVLink)
@@ -102,7 +116,7 @@ struct Ctx {
     drs_i64 L;
     // one stage = one plane of the tile (+ halo); called by thread 0 (TMA) or by every thread of the CTA (DRS_FLAT)
     __device__ __forceinline__ void issue(int n) const {
-        const int s = n & (ST - 1);
+        const int s = ring_slot(n);
 #if DRS_FLAT
         const drs_i64 z = (drs_i64)z0 + n;
         flat_fill<YB, WB, NW * 32>(reinterpret_cast<real*>(ring + s * PLANE_STRIDE), in + z * M * N, z >= 0 && z < L, M, N, y_box, x_box,
@@ -122,8 +136,8 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
         // ---- source plane of level s-1 as this thread sees it: own rows/columns + neighbours ----
         const real* src;
         if (s == 1) {
-            if (!mbar_wait(&c.bars[n & (ST - 1)], (drs_u32)((n / ST) & 1), c.fault)) return false;
-            src = reinterpret_cast<const real*>(c.ring + (n & (ST - 1)) * PLANE_STRIDE);
+            if (!mbar_wait(&c.bars[ring_slot(n)], ring_phase(n), c.fault)) return false;
+            src = reinterpret_cast<const real*>(c.ring + ring_slot(n) * PLANE_STRIDE);
         } else {
             src = reinterpret_cast<const real*>(c.lv + ((s >= 2 ? s - 2 : 0) * 2 + ((n + 1) & 1)) * PLANE_STRIDE);
         }
@@ -219,6 +233,44 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
             }
         } else if (n >= c.n_first && n < c.n_end) {
             const drs_i64 z = c.z_out0 + n;
+#if DRS_T3_LEANSTORE
+            unsigned int sm = c.smask;
+            asm volatile("" : "+r"(sm));      // tested bit by bit where it is used: unpacked into one register per row it costs spills
+            auto scaled = [&](int y, int v) {
+#ifdef DRS_OUT_SCALE
+                return rmul(pw[TS - 1][mod_k2(PH - RK)][y][v], (real)DRS_OUT_SCALE);
+#else
+                return pw[TS - 1][mod_k2(PH - RK)][y][v];
+#endif
+            };
+            auto store_plane = [&](real* base) {
+                if ((sm >> 8) == (unsigned int)(kVec << 8)) {           // whole vectors: every tile away from the grid edge
+#pragma unroll
+                    for (int y = 0; y < RY; ++y) {
+                        real o[kVec];
+#pragma unroll
+                        for (int v = 0; v < kVec; ++v) o[v] = scaled(y, v);
+                        if ((sm >> y) & 1u) stg_vec(base + (drs_i64)y * c.N, o);
+                    }
+                } else {
+                    const int vl = (int)((sm >> 8) & 0xffu), vh = (int)(sm >> 16);
+#pragma unroll
+                    for (int y = 0; y < RY; ++y)
+#pragma unroll
+                        for (int v = 0; v < kVec; ++v)
+                            if (((sm >> y) & 1u) && v >= vl && v < vh) base[(drs_i64)y * c.N + v] = scaled(y, v);
+                }
+            };
+            real* const own = c.optr + (drs_i64)n * (c.M * c.N);
+            store_plane(own);
+            // the same cell of a neighbour's array: byte distance between the two allocations + the plane shift
+            auto in_peer = [&](real* peer, drs_i64 shift) {
+                return reinterpret_cast<real*>(reinterpret_cast<char*>(own) +
+                                               (reinterpret_cast<const char*>(peer) - reinterpret_cast<const char*>(c.out))) + shift * c.M * c.N;
+            };
+            if (c.peer_lo != nullptr && z >= c.lo0 && z < c.lo1) store_plane(in_peer(c.peer_lo, c.lo_shift));
+            if (c.peer_hi != nullptr && z >= c.hi0 && z < c.hi1) store_plane(in_peer(c.peer_hi, c.hi_shift));
+#else
             const drs_i64 row0 = c.y_first * c.N + c.x_first;
             // one pass per destination (own array, then the neighbours' ghost planes on the boundary planes of a slab):
             // a single base pointer is live at a time -- with all three live the slab entry point spilled in this loop
@@ -250,6 +302,7 @@ __device__ __forceinline__ bool iteration(real (&pw)[TS][K2][RY][kVec], const Ct
             store_plane(c.out + z * c.M * c.N + row0);
             if (c.peer_lo != nullptr && z >= c.lo0 && z < c.lo1) store_plane(c.peer_lo + (z + c.lo_shift) * c.M * c.N + row0);
             if (c.peer_hi != nullptr && z >= c.hi0 && z < c.hi1) store_plane(c.peer_hi + (z + c.hi_shift) * c.M * c.N + row0);
+#endif
         }
     }
     // published planes visible to every warp; the input stage is consumed by all of them
@@ -339,6 +392,15 @@ __device__ __forceinline__ void sweep(const TensorMap& tmap, const Params& p) {
     c.in = p.in;
     c.L = p.L;
     c.out = p.out;
+    {
+        unsigned int rows = 0u;
+#pragma unroll
+        for (int y = 0; y < RY; ++y)
+            if (y >= c.y_lo && y < c.y_hi) rows |= 1u << y;
+        const int vl = clampi(c.v_lo, 0, kVec), vh = clampi(c.v_hi, 0, kVec);
+        c.smask = vl < vh ? (rows | ((unsigned int)vl << 8) | ((unsigned int)vh << 16)) : 0u;
+        c.optr = p.out + (c.z_out0 * p.M + c.y_first) * p.N + c.x_first;
+    }
     c.peer_lo = p.peer_lo;
     c.peer_hi = p.peer_hi;
     c.lo0 = p.push_lo0; c.lo1 = p.push_lo1; c.lo_shift = p.peer_lo_shift;
