@@ -76,3 +76,37 @@ def test_tile_overrides_compile(built, name, kn):
     allowed = 64 if name.startswith("3d") and kn.get("step", 1) > 1 else 0     # fused 3D kernel at its 128-register cap
     assert plan.info.kernel_name.startswith("dr_") and regs <= 255 and spill <= allowed, (kn, regs, spill)
     assert plan.info.smem_bytes <= 227 * 1024
+
+
+def test_fused_temporal_ring_takes_any_depth(built):
+    """`--stages n` of the fused 3D temporal kernel is not rounded to a power of two (the other kernels' rings are);
+    profiles/r02_temporal3d_ring_depth.txt is the measurement that made two stages the default."""
+    import drstencil_b200 as drs
+    for stages, want in ((2, 2), (3, 3), (5, 5)):
+        plan = drs.Plan(drs.Stencil.from_file(stc_path("3d7pt_star")).set_size((96, 200, 264)), drs.Knobs(step=2, stages=stages))
+        assert "drs_sweep3d_t.cuh" in plan.source and "#define DRS_ST %d\n" % want in plan.source
+        assert plan.info.stages == want
+        regs, spill = _resources(plan)
+        assert regs <= 128 and spill == 0
+    single = drs.Plan(drs.Stencil.from_file(stc_path("3d7pt_star")).set_size((96, 200, 264)), drs.Knobs(stages=5))
+    assert "#define DRS_ST 8\n" in single.source
+
+
+def test_l2_policy_only_on_large_3d_arrays(built, monkeypatch):
+    """Plane loads carry the L2 evict_last policy (DRS_LD_HINT 1 -> cp.async.bulk.tensor ... .L2::cache_hint) only where
+    nothing of one sweep survives in the L2 until the next: 3D arrays of 1 GiB and more on the TMA path."""
+    import drstencil_b200 as drs
+
+    def src(name, shape, **kn):
+        return drs.Plan(drs.Stencil.from_file(stc_path(name)).set_size(shape), drs.Knobs(**kn)).source
+
+    big, small = (512, 512, 512), (96, 200, 264)
+    for kn in (dict(), dict(step=2), dict(share_x=2, share_y=2, rows_3d=8, bx=32, by=4)):
+        assert "#define DRS_LD_HINT 1" in src("3d7pt_star", big, **kn)
+        assert "DRS_LD_HINT" not in src("3d7pt_star", small, **kn)
+    assert "#define DRS_LD_HINT 1" in src("3d7pt_star", (648, 648, 648), dtype="f32")        # 1.01 GiB of fp32
+    assert "DRS_LD_HINT" not in src("3d7pt_star", (512, 512, 512), dtype="f32")              # 0.5 GiB
+    assert "DRS_LD_HINT" not in src("3d7pt_star", (512, 512, 513))                           # unaligned pitch: no 3D TMA boxes
+    assert "DRS_LD_HINT" not in src("2d5pt_star", (16384, 16384))
+    monkeypatch.setenv("DRS_NO_LD_HINT", "1")
+    assert "DRS_LD_HINT" not in src("3d7pt_star", big)
